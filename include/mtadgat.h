@@ -1,0 +1,99 @@
+/* mtadgat.h -- C ABI of libmtadgat.so, the B200 (sm_100a) hot path of MTAD-GAT.
+ *
+ * The reference (ML4ITS/mtad-gat-pytorch) has no FFI: its boundary for this path is the set of Python
+ * nn.Module classes in modules.py / mtad_gat.py.  Each entry point below replaces the arithmetic of one of
+ * those classes' forward (and the autograd backward torch derives for it); the citation after each
+ * declaration is the reference file:line it stands in for.  The Python host side
+ * (mtad_gat_pytorch_b200/modules.py) mirrors the reference classes and calls these through ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 unless stated otherwise; sizes are ints
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *   - return value 0 = ok; non-zero = error, message via mtadgat_last_error() (thread-local)
+ *   - `saved` buffers are written by *_fwd and must be handed unchanged to the matching *_bwd;
+ *     `scratch` buffers are temporaries; sizes (in floats) come from the *_floats() queries
+ *   - dropout: multipliers are a pure function of (*seed, rng stream id, element index) (Philox4x32-10), so
+ *     forward and backward regenerate the same mask; `seed` points to a device uint64 (CUDA-graph safe)
+ *   - gradients of parameters are overwritten (not accumulated); data gradients honour `*_accumulate`
+ */
+#ifndef MTADGAT_H_
+#define MTADGAT_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTADGAT_ABI_VERSION 1
+
+const char* mtadgat_last_error(void);
+int mtadgat_abi_version(void);
+unsigned long long mtadgat_launch_count(void);     /* kernels launched by this library so far */
+void mtadgat_reset_launch_count(void);
+
+/* ---- ConvLayer.forward: modules.py:18-22 (pad, Conv1d, ReLU; x,y are (B,n,k); w (k,k,ks); odd ks) ---- */
+int mtadgat_conv_relu_fwd(const float* x, const float* w, const float* bias, float* y, int B, int n, int k, int ks,
+                          void* stream);
+int mtadgat_conv_relu_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx /*nullable*/,
+                          float* dw, float* db, int B, int n, int k, int ks, void* stream);
+
+/* ---- FeatureAttentionLayer.forward modules.py:65-95 (feature=1) / TemporalAttentionLayer.forward
+ *      modules.py:166-193 (feature=0).  E = lin.weight.shape[0]; GATv2: lin_w (E,2D), a (E); GATv1: lin_w (E,D),
+ *      a (2E); D = n (feature) or k (temporal); bias (K,K) nullable; out (B,n,k).
+ *      save_att=1 keeps the attention matrix in `saved` for backward; p_drop = attention dropout
+ *      (0 in eval mode).  rng stream ids 1 (feature) and 2 (temporal) are used internally. ---- */
+long long mtadgat_gat_saved_floats(int B, int n, int k, int E, int feature, int use_gatv2, int save_att);
+long long mtadgat_gat_bwd_scratch_floats(int B, int n, int k, int E, int feature, int use_gatv2);
+int mtadgat_gat_fwd(const float* x, const float* lin_w, const float* lin_b, const float* a, const float* bias,
+                    float* out, float* saved, int B, int n, int k, int E, int feature, int use_gatv2, float alpha,
+                    int save_att, float p_drop, const unsigned long long* seed, void* stream);
+int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* lin_b, const float* a, const float* out,
+                    const float* gout, const float* saved, float* scratch, float* dx, int dx_accumulate,
+                    float* dlin_w, float* dlin_b, float* da, float* dbias /*nullable*/, int B, int n, int k, int E,
+                    int feature, int use_gatv2, float alpha, float p_drop, const unsigned long long* seed,
+                    void* stream);
+
+/* ---- GRULayer.forward modules.py:235-238 (one nn.GRU layer, batch_first, h0=0, gate order r,z,n).
+ *      The input is given as up to three column slices x0|x1|x2 of widths k0,k1,k2 (the torch.cat of
+ *      mtad_gat.py:71 is never materialised).  out (B,n,H) nullable when save=0; h_last (B,H) nullable. ---- */
+long long mtadgat_gru_saved_floats(int B, int n, int H, int save);
+long long mtadgat_gru_fwd_scratch_floats(int B, int n, int H);
+long long mtadgat_gru_bwd_scratch_floats(int B, int n, int H);
+int mtadgat_gru_fwd(const float* x0, const float* x1, const float* x2, int k0, int k1, int k2, const float* w_ih,
+                    const float* w_hh, const float* b_ih, const float* b_hh, float* out, float* h_last, float* saved,
+                    float* scratch, int B, int n, int H, int save, void* stream);
+int mtadgat_gru_bwd(const float* x0, const float* x1, const float* x2, int k0, int k1, int k2, const float* w_ih,
+                    const float* w_hh, const float* out, const float* saved, const float* dout /*nullable*/,
+                    const float* dh_last /*nullable*/, float* scratch, float* dx0, float* dx1, float* dx2, int acc0,
+                    int acc1, int acc2, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int B, int n, int H,
+                    void* stream);
+
+/* ---- ReconstructionModel.forward modules.py:276-281: decoder GRU over the reference's scrambled repeat
+ *      rep[b,t,c] = h_src[b,(t*Hs+c)//n] (modules.py:279), all n outputs (B,n,R). ---- */
+int mtadgat_rep_J(int n, int Hs);
+long long mtadgat_gru_rep_saved_floats(int B, int n, int Hs, int R, int save);
+long long mtadgat_gru_rep_bwd_scratch_floats(int B, int n, int Hs, int R);
+int mtadgat_gru_rep_fwd(const float* h_src, const float* w_ih, const float* w_hh, const float* b_ih,
+                        const float* b_hh, float* out, float* saved, int B, int n, int Hs, int R, int save,
+                        void* stream);
+int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const float* w_hh, const float* out,
+                        const float* saved, const float* dout, float* scratch, float* dh_src, int dh_accumulate,
+                        float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int B, int n, int Hs, int R,
+                        void* stream);
+
+/* ---- nn.Linear (+ReLU, +Dropout): Forecasting_Model.forward modules.py:307-311, recon fc modules.py:282.
+ *      x (M,I), w (O,I), b (O), y (M,O); act 0 none / 1 relu. ---- */
+int mtadgat_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int I, int O, int act,
+                       float p_drop, const unsigned long long* seed, unsigned int rng_stream, void* stream);
+int mtadgat_linear_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx /*nullable*/,
+                       int dx_accumulate, float* dw, float* db, int M, int I, int O, int act, float p_drop,
+                       const unsigned long long* seed, unsigned int rng_stream, void* stream);
+
+/* ---- RNG plumbing ---- */
+int mtadgat_dropout_mask(float* out, long long numel, float p, const unsigned long long* seed,
+                         unsigned int rng_stream, void* stream);   /* multipliers 0 or 1/(1-p), for tests */
+int mtadgat_seed_advance(unsigned long long* seed, void* stream);  /* new seed per step, on device */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MTADGAT_H_ */

@@ -1,0 +1,70 @@
+"""ctypes binding of libmtadgat.so (C ABI declared in include/mtadgat.h).
+
+The library is the product: if it is missing or fails to load, importing this module raises -- there is
+no CPU or eager-PyTorch fallback anywhere in the package.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmtadgat.so")
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+_U = ctypes.c_uint
+_LL = ctypes.c_longlong
+
+# name -> (restype, argtypes); mirrors include/mtadgat.h one to one
+SIGNATURES = {
+    "mtadgat_last_error": (ctypes.c_char_p, []),
+    "mtadgat_abi_version": (_I, []),
+    "mtadgat_launch_count": (ctypes.c_ulonglong, []),
+    "mtadgat_reset_launch_count": (None, []),
+    "mtadgat_conv_relu_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mtadgat_conv_relu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mtadgat_gat_saved_floats": (_LL, [_I, _I, _I, _I, _I, _I, _I]),
+    "mtadgat_gat_bwd_scratch_floats": (_LL, [_I, _I, _I, _I, _I, _I]),
+    "mtadgat_gat_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _P, _P]),
+    "mtadgat_gat_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P]),
+    "mtadgat_gru_saved_floats": (_LL, [_I, _I, _I, _I]),
+    "mtadgat_gru_fwd_scratch_floats": (_LL, [_I, _I, _I]),
+    "mtadgat_gru_bwd_scratch_floats": (_LL, [_I, _I, _I]),
+    "mtadgat_gru_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mtadgat_gru_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I,
+                             _P, _P, _P, _P, _I, _I, _I, _P]),
+    "mtadgat_rep_J": (_I, [_I, _I]),
+    "mtadgat_gru_rep_saved_floats": (_LL, [_I, _I, _I, _I, _I]),
+    "mtadgat_gru_rep_bwd_scratch_floats": (_LL, [_I, _I, _I, _I]),
+    "mtadgat_gru_rep_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "mtadgat_gru_rep_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mtadgat_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _U, _P]),
+    "mtadgat_linear_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _F, _P, _U, _P]),
+    "mtadgat_dropout_mask": (_I, [_P, _LL, _F, _P, _U, _P]),
+    "mtadgat_seed_advance": (_I, [_P, _P]),
+}
+
+
+class MtadGatLibraryError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise MtadGatLibraryError(
+            f"{LIB_PATH} not found: build the sm_100a library first (python __graft_entry__.py build). "
+            "mtad_gat_pytorch_b200 has no CPU / eager fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)       # AttributeError here = header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    if rc != 0:
+        raise MtadGatLibraryError(lib.mtadgat_last_error().decode("utf-8", "replace"))

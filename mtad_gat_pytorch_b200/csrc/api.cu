@@ -1,0 +1,51 @@
+// Library-level entry points: error reporting, launch counter, dropout-mask probe.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+#include "../../include/mtadgat.h"
+
+static thread_local char g_err[512] = "";
+unsigned long long g_mtadgat_launches = 0;
+
+void mtadgat_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* mtadgat_last_error(void) { return g_err; }
+extern "C" int mtadgat_abi_version(void) { return MTADGAT_ABI_VERSION; }
+extern "C" unsigned long long mtadgat_launch_count(void) { return g_mtadgat_launches; }
+extern "C" void mtadgat_reset_launch_count(void) { g_mtadgat_launches = 0; }
+
+namespace {
+__global__ void dropout_mask_kernel(float* out, long long numel, float p, float inv_keep,
+                                    const unsigned long long* seed, uint32_t stream) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < numel) out[i] = dropout_mult(seed, stream, (unsigned long long)i, p, inv_keep);
+}
+__global__ void seed_advance_kernel(unsigned long long* seed) {
+  // splitmix64 step: a fresh, well-mixed seed per training step, graph-replay safe (state lives in HBM)
+  unsigned long long z = (*seed += 0x9E3779B97F4A7C15ull);
+  (void)z;
+}
+}  // namespace
+
+extern "C" int mtadgat_dropout_mask(float* out, long long numel, float p, const unsigned long long* seed,
+                                    unsigned int rng_stream, void* stream) {
+  MG_CHECK_ARG(out && seed && numel >= 0 && p >= 0.f && p < 1.f, "dropout_mask: bad arguments");
+  if (numel == 0) return MTADGAT_OK;
+  dropout_mask_kernel<<<cdiv(numel, 256), 256, 0, (cudaStream_t)stream>>>(out, numel, p, 1.f / (1.f - p), seed, rng_stream);
+  MG_COUNT_LAUNCH();
+  MG_CHECK_LAUNCH("dropout_mask");
+  return MTADGAT_OK;
+}
+
+extern "C" int mtadgat_seed_advance(unsigned long long* seed, void* stream) {
+  MG_CHECK_ARG(seed, "seed_advance: null pointer");
+  seed_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(seed);
+  MG_COUNT_LAUNCH();
+  MG_CHECK_LAUNCH("seed_advance");
+  return MTADGAT_OK;
+}

@@ -1,0 +1,780 @@
+// FeatureAttentionLayer / TemporalAttentionLayer (reference modules.py:25-122 / 125-217), GATv2 and GATv1.
+//
+// The reference materialises a (B,K,K,2D) tensor of all node pairs and runs a Linear over it.  Here
+//   lin([v_i || v_j]) = W1 v_i + W2 v_j + b                         (W = [W1 | W2] split on input columns)
+// so only two (K x D)(D x E) projections per window are needed, and
+//   a^T lrelu_alpha(z) = alpha * a^T z + sum_d |c_d| sign(a_d) relu(z_d),   c_d = (1-alpha) a_d
+// so with the columns of the projection pre-scaled by |c_d| and sorted by sign(a_d) the K*K*E score build
+// is one add + one max + one accumulate per element:
+//   e_ij = alpha (p_i + q_j) + sum_{d<npos} max(P_id+Q_jd,0) - sum_{d>=npos} max(P_id+Q_jd,0) + bias_ij
+// GATv1 (e_ij = lrelu(s_i + t_j)) is the E=0 case of the same kernels.
+//
+// Layouts: window tensor x (B,n,k) read in place (nodes = features for the feature layer, = timestamps for
+// the temporal layer).  Projections are stored channel-major PQt (B, NC, Kp), NC = 2E+2, Kp = K rounded
+// up to 4, channels [P(E) | Q(E) | p | q].  Attention (B,K,Kp) is kept only in training.
+#include "gemm.cuh"
+#include "../../include/mtadgat.h"
+
+namespace {
+
+struct GatDims {
+  int B, n, k, K, D, E, NC, Kp, feature, v2;
+};
+
+static GatDims make_dims(int B, int n, int k, int E, int feature, int v2) {
+  GatDims d;
+  d.B = B; d.n = n; d.k = k; d.feature = feature; d.v2 = v2;
+  d.K = feature ? k : n; d.D = feature ? n : k;
+  d.E = v2 ? E : 0;               // width of the P/Q blocks (v1 keeps only the rank-1 channels)
+  d.NC = 2 * d.E + 2;
+  d.Kp = (d.K + 3) & ~3;
+  return d;
+}
+
+// saved-buffer layout (floats)
+struct SavedLayout {
+  size_t wp, bp, meta, pqt, att, total;
+};
+static SavedLayout saved_layout(const GatDims& d, int Eraw, int training) {
+  SavedLayout L;
+  size_t o = 0;
+  L.wp = o; o += (size_t)d.D * d.NC;
+  L.bp = o; o += (size_t)d.NC;
+  o = (o + 3) & ~(size_t)3;
+  L.meta = o; o += (size_t)(2 * Eraw + 4);
+  o = (o + 3) & ~(size_t)3;
+  L.pqt = o; o += (size_t)d.B * d.NC * d.Kp;
+  L.att = o; if (training) o += (size_t)d.B * d.K * d.Kp;
+  L.total = o;
+  return L;
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: fold a, alpha into the projection weights
+// ---------------------------------------------------------------------------------------------
+// meta ints: [0]=npos, [4 .. 4+E) = perm (sorted position -> original column), [4+E .. 4+2E) = inverse
+__global__ void gat_prep_perm_kernel(const float* __restrict__ a, int E, int* __restrict__ meta) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int np = 0;
+  for (int e = 0; e < E; ++e)
+    if (a[e] > 0.f) { meta[4 + np] = e; meta[4 + E + e] = np; ++np; }
+  meta[0] = np;
+  int q = np;
+  for (int e = 0; e < E; ++e)
+    if (!(a[e] > 0.f)) { meta[4 + q] = e; meta[4 + E + e] = q; ++q; }
+}
+
+// v2: lin_w (E, 2D), lin_b (E), a (E).   v1: lin_w (E, D), lin_b (E), a (2E).
+__global__ void gat_prep_fill_kernel(const float* __restrict__ lin_w, const float* __restrict__ lin_b,
+                                     const float* __restrict__ a, const int* __restrict__ meta, float alpha, int D,
+                                     int Eraw, int v2, float* __restrict__ wp, float* __restrict__ bp) {
+  const int NC = v2 ? 2 * Eraw + 2 : 2;
+  const int E = v2 ? Eraw : 0;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = (D + 1) * NC;  // row D is the bias row
+  if (idx >= total) return;
+  int dd = idx / NC, c = idx - dd * NC;
+  float v;
+  if (c < 2 * E) {
+    int half = c >= E, ep = c - half * E;
+    int e = meta[4 + ep];
+    float s = fabsf(a[e]) * (1.f - alpha);
+    if (dd < D) v = s * lin_w[(long long)e * 2 * D + half * D + dd];
+    else v = half ? s * lin_b[e] : 0.f;
+  } else {
+    int half = c - 2 * E;
+    float acc = 0.f;
+    if (v2) {
+      if (dd < D) for (int e = 0; e < Eraw; ++e) acc += a[e] * lin_w[(long long)e * 2 * D + half * D + dd];
+      else if (half) for (int e = 0; e < Eraw; ++e) acc += a[e] * lin_b[e];
+    } else {
+      const float* ah = a + half * Eraw;
+      if (dd < D) for (int e = 0; e < Eraw; ++e) acc += ah[e] * lin_w[(long long)e * D + dd];
+      else for (int e = 0; e < Eraw; ++e) acc += ah[e] * lin_b[e];
+    }
+    v = acc;
+  }
+  if (dd < D) wp[(long long)dd * NC + c] = v;
+  else bp[c] = v;
+}
+
+// one warp per original column e: chain dWp/dbp back to lin_w, lin_b, a
+__global__ void gat_prep_bwd_kernel(const float* __restrict__ lin_w, const float* __restrict__ lin_b,
+                                    const float* __restrict__ a, const int* __restrict__ meta, float alpha, int D,
+                                    int Eraw, int v2, const float* __restrict__ dwp, const float* __restrict__ dbp,
+                                    float* __restrict__ dlin_w, float* __restrict__ dlin_b, float* __restrict__ da) {
+  int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (e >= Eraw) return;
+  if (v2) {
+    const int E = Eraw, NC = 2 * E + 2;
+    int ep = meta[4 + E + e];
+    float ae = a[e], s = fabsf(ae) * (1.f - alpha), sg = (ae > 0.f) ? (1.f - alpha) : -(1.f - alpha);
+    float accs = 0.f, accr = 0.f;
+    for (int dd = lane; dd < D; dd += 32) {
+      float w1 = lin_w[(long long)e * 2 * D + dd], w2 = lin_w[(long long)e * 2 * D + D + dd];
+      float g1 = dwp[(long long)dd * NC + ep], g2 = dwp[(long long)dd * NC + E + ep];
+      float r1 = dwp[(long long)dd * NC + 2 * E], r2 = dwp[(long long)dd * NC + 2 * E + 1];
+      dlin_w[(long long)e * 2 * D + dd] = s * g1 + ae * r1;
+      dlin_w[(long long)e * 2 * D + D + dd] = s * g2 + ae * r2;
+      accs += w1 * g1 + w2 * g2;
+      accr += w1 * r1 + w2 * r2;
+    }
+    accs = warp_sum(accs); accr = warp_sum(accr);
+    if (lane == 0) {
+      float be = lin_b[e];
+      dlin_b[e] = s * dbp[E + ep] + ae * dbp[2 * E + 1];
+      da[e] = sg * (accs + be * dbp[E + ep]) + accr + be * dbp[2 * E + 1];
+    }
+  } else {
+    float a1 = a[e], a2 = a[Eraw + e];
+    float acc1 = 0.f, acc2 = 0.f;
+    for (int dd = lane; dd < D; dd += 32) {
+      float w = lin_w[(long long)e * D + dd];
+      float r1 = dwp[(long long)dd * 2 + 0], r2 = dwp[(long long)dd * 2 + 1];
+      dlin_w[(long long)e * D + dd] = a1 * r1 + a2 * r2;
+      acc1 += w * r1; acc2 += w * r2;
+    }
+    acc1 = warp_sum(acc1); acc2 = warp_sum(acc2);
+    if (lane == 0) {
+      float be = lin_b[e];
+      dlin_b[e] = a1 * dbp[0] + a2 * dbp[1];
+      da[e] = acc1 + be * dbp[0];
+      da[Eraw + e] = acc2 + be * dbp[1];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// functors for the projection GEMMs
+// ---------------------------------------------------------------------------------------------
+// V(b,node,dd) in the window layout
+template <bool FEATURE>
+__device__ __forceinline__ long long node_off(int b, int node, int dd, int n, int k) {
+  return FEATURE ? ((long long)b * n + dd) * k + node : ((long long)b * n + node) * k + dd;
+}
+
+// projection forward: PQt[b][c][node] = sum_dd Wp[dd][c] * V(b,node,dd) + bp[c]
+//   A(m=c, kk=dd) = Wp[dd*NC + c]   (m-fast)
+struct WpT {
+  static constexpr bool fast_second = false;
+  const float* wp; int NC;
+  __device__ __forceinline__ float operator()(int, int c, int dd) const { return __ldg(wp + (long long)dd * NC + c); }
+};
+//   B(z=b, kk=dd, n=node) = V(b,node,dd):   feature -> node-fast, temporal -> dd-fast
+template <bool FEATURE>
+struct NodeB {
+  static constexpr bool fast_second = FEATURE;
+  const float* x; int n, k;
+  __device__ __forceinline__ float operator()(int b, int dd, int node) const {
+    return __ldg(x + node_off<FEATURE>(b, node, dd, n, k));
+  }
+};
+struct StPQt {
+  float* pqt; const float* bp; int NC, Kp;
+  __device__ __forceinline__ void operator()(int b, int c, int node, float v, bool) const {
+    pqt[((long long)b * NC + c) * Kp + node] = v + __ldg(bp + c);
+  }
+};
+
+// dWp[dd][c] = sum_{b,node} V(b,node,dd) dPQt[b][c][node]      (split-K over kk=(b,node))
+template <bool FEATURE>
+struct NodeAT {
+  static constexpr bool fast_second = FEATURE;   // feature: kk(node)-fast ; temporal: m(dd)-fast
+  const float* x; int n, k, K;
+  __device__ __forceinline__ float operator()(int, int dd, int kk) const {
+    int b = kk / K, node = kk - b * K;
+    return __ldg(x + node_off<FEATURE>(b, node, dd, n, k));
+  }
+};
+struct DpqB {
+  static constexpr bool fast_second = false;     // kk(node)-fast
+  const float* dpqt; int NC, Kp, K;
+  __device__ __forceinline__ float operator()(int, int kk, int c) const {
+    int b = kk / K, node = kk - b * K;
+    return __ldg(dpqt + ((long long)b * NC + c) * Kp + node);
+  }
+};
+// dbp[c] = sum_{b,node} dPQt[b][c][node]
+struct DpqCols {
+  static constexpr bool fast_second = false;
+  const float* dpqt; int NC, Kp, K;
+  __device__ __forceinline__ float operator()(int, int m, int c) const {
+    int b = m / K, node = m - b * K;
+    return __ldg(dpqt + ((long long)b * NC + c) * Kp + node);
+  }
+};
+// dV(b,node,dd) += sum_c dPQt[b][c][node] Wp[dd][c]    batched over b
+struct DpqA {
+  static constexpr bool fast_second = false;     // m(node)-fast
+  const float* dpqt; int NC, Kp;
+  __device__ __forceinline__ float operator()(int b, int node, int c) const {
+    return __ldg(dpqt + ((long long)b * NC + c) * Kp + node);
+  }
+};
+struct WpB {
+  static constexpr bool fast_second = false;     // kk(c)-fast
+  const float* wp; int NC;
+  __device__ __forceinline__ float operator()(int, int c, int dd) const { return __ldg(wp + (long long)dd * NC + c); }
+};
+template <bool FEATURE>
+struct StNodeAcc {
+  float* dx; int n, k; int accumulate;
+  __device__ __forceinline__ void operator()(int b, int node, int dd, float v, bool) const {
+    float* q = dx + node_off<FEATURE>(b, node, dd, n, k);
+    *q = accumulate ? (*q + v) : v;
+  }
+};
+// dV(b,j,dd) += sum_i att~[b][i][j] dS[b][i][dd]     batched over b;  att~ = att * dropout multiplier
+struct AttTA {
+  static constexpr bool fast_second = false;     // m(j)-fast
+  const float* att; int K, Kp; float p, inv_keep; const unsigned long long* seed; uint32_t stream;
+  __device__ __forceinline__ float operator()(int b, int j, int i) const {
+    float v = __ldg(att + ((long long)b * K + i) * Kp + j);
+    if (p > 0.f) v *= dropout_mult(seed, stream, ((unsigned long long)b * K + i) * K + j, p, inv_keep);
+    return v;
+  }
+};
+struct DsB {
+  static constexpr bool fast_second = true;
+  const float* ds; int K, D;
+  __device__ __forceinline__ float operator()(int b, int i, int dd) const {
+    return __ldg(ds + ((long long)b * K + i) * D + dd);
+  }
+};
+// dbias[i][j] = sum_b de[b][i][j]
+struct DeCols {
+  static constexpr bool fast_second = true;
+  const float* de; int K, Kp;
+  __device__ __forceinline__ float operator()(int, int b, int ij) const {
+    int i = ij / K, j = ij - i * K;
+    return __ldg(de + ((long long)b * K + i) * Kp + j);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// fused score -> softmax -> dropout -> aggregate -> sigmoid       (one CTA = one window x RB rows)
+// ---------------------------------------------------------------------------------------------
+struct ScoreParams {
+  const float* x; const float* pqt; const float* bias; const int* meta;
+  float* out; float* att;
+  int n, k, K, D, E, NC, Kp;
+  int RB, JT, DT;          // row block, column tile, channel tile
+  int feature, v2;
+  float alpha, p, inv_keep; const unsigned long long* seed; uint32_t stream;
+};
+
+template <int MI, int MJ>
+__global__ void __launch_bounds__(256) gat_score_fwd_kernel(ScoreParams P) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.y, i0 = blockIdx.x * P.RB;
+  const int rb = min(P.RB, P.K - i0);
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int K = P.K, Kp = P.Kp, E = P.E, D = P.D;
+  const int RBp = (P.RB + 3) & ~3, JTp = (P.JT + 3) & ~3;
+  float* sS = smem;                          // [RB][Kp] scores / attention
+  float* sP = sS + (size_t)P.RB * Kp;        // [DT][RBp]
+  float* sQ = sP + (size_t)P.DT * RBp;       // [DT][JTp]   (later reused as V tile [JT][D+1])
+  const float* pq = P.pqt + (size_t)b * P.NC * Kp;
+  const int npos = P.v2 ? P.meta[0] : 0;
+
+  // ---- init scores with the rank-1 part + bias -------------------------------------------------
+  for (int idx = tid; idx < rb * K; idx += nth) {
+    int i = idx / K, j = idx - i * K;
+    float pi = pq[(size_t)(2 * E) * Kp + i0 + i], qj = pq[(size_t)(2 * E + 1) * Kp + j];
+    float s = pi + qj;
+    float e = P.v2 ? P.alpha * s : (s > 0.f ? s : P.alpha * s);
+    if (P.bias) e += __ldg(P.bias + (size_t)(i0 + i) * K + j);
+    sS[i * Kp + j] = e;
+  }
+  // ---- GATv2 K*K*E part -----------------------------------------------------------------------
+  if (E > 0) {
+    const int nti = (rb + MI - 1) / MI;
+    for (int j0 = 0; j0 < K; j0 += P.JT) {
+      const int jt = min(P.JT, K - j0);
+      const int ntj = (jt + MJ - 1) / MJ;
+      const int nmt = nti * ntj;
+      for (int d0 = 0; d0 < E; d0 += P.DT) {
+        const int dt = min(P.DT, E - d0);
+        __syncthreads();
+        for (int idx = tid; idx < dt * RBp; idx += nth) {
+          int d = idx / RBp, i = idx - d * RBp;
+          sP[idx] = (i < rb) ? pq[(size_t)(d0 + d) * Kp + i0 + i] : 0.f;
+        }
+        for (int idx = tid; idx < dt * JTp; idx += nth) {
+          int d = idx / JTp, j = idx - d * JTp;
+          sQ[idx] = (j < jt) ? pq[(size_t)(E + d0 + d) * Kp + j0 + j] : 0.f;
+        }
+        __syncthreads();
+        const int dsplit = max(0, min(dt, npos - d0));
+        for (int mt = tid; mt < nmt; mt += nth) {
+          const int ti = mt / ntj, tj = mt - ti * ntj;
+          const float* pp = sP + ti * MI;
+          const float* qq = sQ + tj * MJ;
+          float accp[MI][MJ], accn[MI][MJ];
+#pragma unroll
+          for (int a = 0; a < MI; ++a)
+#pragma unroll
+            for (int c = 0; c < MJ; ++c) { accp[a][c] = 0.f; accn[a][c] = 0.f; }
+          int d = 0;
+          for (; d < dsplit; ++d) {
+            float pv[MI], qv[MJ];
+#pragma unroll
+            for (int a = 0; a < MI; ++a) pv[a] = pp[d * RBp + a];
+#pragma unroll
+            for (int c = 0; c < MJ; ++c) qv[c] = qq[d * JTp + c];
+#pragma unroll
+            for (int a = 0; a < MI; ++a)
+#pragma unroll
+              for (int c = 0; c < MJ; ++c) accp[a][c] += fmaxf(pv[a] + qv[c], 0.f);
+          }
+          for (; d < dt; ++d) {
+            float pv[MI], qv[MJ];
+#pragma unroll
+            for (int a = 0; a < MI; ++a) pv[a] = pp[d * RBp + a];
+#pragma unroll
+            for (int c = 0; c < MJ; ++c) qv[c] = qq[d * JTp + c];
+#pragma unroll
+            for (int a = 0; a < MI; ++a)
+#pragma unroll
+              for (int c = 0; c < MJ; ++c) accn[a][c] += fmaxf(pv[a] + qv[c], 0.f);
+          }
+#pragma unroll
+          for (int a = 0; a < MI; ++a) {
+            int i = ti * MI + a;
+            if (i >= rb) continue;
+#pragma unroll
+            for (int c = 0; c < MJ; ++c) {
+              int j = tj * MJ + c;
+              if (j < jt) sS[i * Kp + j0 + j] += accp[a][c] - accn[a][c];
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- row softmax (one warp per row), save attention, apply dropout --------------------------
+  {
+    const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+    for (int i = warp; i < rb; i += nw) {
+      float* row = sS + i * Kp;
+      float m = -INFINITY;
+      for (int j = lane; j < K; j += 32) m = fmaxf(m, row[j]);
+      m = warp_max(m);
+      float s = 0.f;
+      for (int j = lane; j < K; j += 32) { float ex = __expf(row[j] - m); row[j] = ex; s += ex; }
+      s = warp_sum(s);
+      float inv = 1.f / s;
+      float* arow = P.att ? P.att + ((size_t)b * K + i0 + i) * Kp : nullptr;
+      for (int j = lane; j < K; j += 32) {
+        float av = row[j] * inv;
+        if (arow) arow[j] = av;
+        if (P.p > 0.f)
+          av *= dropout_mult(P.seed, P.stream, ((unsigned long long)b * K + i0 + i) * K + j, P.p, P.inv_keep);
+        row[j] = av;
+      }
+    }
+  }
+  // ---- aggregate S = A~ V, h = sigmoid(S) ------------------------------------------------------
+  {
+    float* sV = sP;                 // [JT][Dp]
+    const int Dp = D + 1;
+    const int ntd = (D + 3) >> 2;
+    const int nmt = ((rb + 3) >> 2) * ntd;     // host guarantees nmt <= blockDim
+    const int ti = tid / ntd, td = tid - ti * ntd;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+    for (int j0 = 0; j0 < K; j0 += P.JT) {
+      const int jt = min(P.JT, K - j0);
+      __syncthreads();
+      if (P.feature) {
+        // V[j][t] = x[b,t,j0+j]
+        for (int idx = tid; idx < jt * D; idx += nth) {
+          int t = idx / jt, j = idx - t * jt;
+          sV[j * Dp + t] = __ldg(P.x + ((size_t)b * P.n + t) * P.k + j0 + j);
+        }
+      } else {
+        for (int idx = tid; idx < jt * D; idx += nth) {
+          int j = idx / D, dd = idx - j * D;
+          sV[j * Dp + dd] = __ldg(P.x + ((size_t)b * P.n + j0 + j) * P.k + dd);
+        }
+      }
+      __syncthreads();
+      if (tid < nmt) {
+        for (int j = 0; j < jt; ++j) {
+          float av[4], vv[4];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) av[a] = (ti * 4 + a < rb) ? sS[(ti * 4 + a) * Kp + j0 + j] : 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) vv[c] = (td * 4 + c < D) ? sV[j * Dp + td * 4 + c] : 0.f;
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][c] = fmaf(av[a], vv[c], acc[a][c]);
+        }
+      }
+    }
+    if (tid < nmt) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        int i = ti * 4 + a;
+        if (i >= rb) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          int dd = td * 4 + c;
+          if (dd >= D) continue;
+          float h = sigmoidf_(acc[a][c]);
+          size_t o = P.feature ? ((size_t)b * P.n + dd) * P.k + i0 + i : ((size_t)b * P.n + i0 + i) * P.k + dd;
+          P.out[o] = h;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward 1: dS = G h (1-h);  dA~ = dS V^T;  de = A (dA - rowdot(A,dA))
+// ---------------------------------------------------------------------------------------------
+struct Bwd1Params {
+  const float* x; const float* out; const float* gout; const float* att;
+  float* ds; float* de;
+  int n, k, K, D, Kp, RB, JT, feature;
+  float p, inv_keep; const unsigned long long* seed; uint32_t stream;
+};
+
+__global__ void __launch_bounds__(256) gat_bwd1_kernel(Bwd1Params P) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.y, i0 = blockIdx.x * P.RB;
+  const int rb = min(P.RB, P.K - i0);
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int K = P.K, Kp = P.Kp, D = P.D, Dp = D + 1;
+  float* sD = smem;                         // [RB][Kp]  dA
+  float* sdS = sD + (size_t)P.RB * Kp;      // [RB][Dp]
+  float* sV = sdS + (size_t)P.RB * Dp;      // [JT][Dp]
+  for (int idx = tid; idx < rb * D; idx += nth) {
+    int i, dd;
+    size_t o;
+    if (P.feature) { dd = idx / rb; i = idx - dd * rb; o = ((size_t)b * P.n + dd) * P.k + i0 + i; }
+    else { i = idx / D; dd = idx - i * D; o = ((size_t)b * P.n + i0 + i) * P.k + dd; }
+    float h = __ldg(P.out + o), g = __ldg(P.gout + o);
+    float v = g * h * (1.f - h);
+    sdS[i * Dp + dd] = v;
+    P.ds[((size_t)b * K + i0 + i) * D + dd] = v;
+  }
+  for (int j0 = 0; j0 < K; j0 += P.JT) {
+    const int jt = min(P.JT, K - j0);
+    __syncthreads();
+    if (P.feature) {
+      for (int idx = tid; idx < jt * D; idx += nth) {
+        int t = idx / jt, j = idx - t * jt;
+        sV[j * Dp + t] = __ldg(P.x + ((size_t)b * P.n + t) * P.k + j0 + j);
+      }
+    } else {
+      for (int idx = tid; idx < jt * D; idx += nth) {
+        int j = idx / D, dd = idx - j * D;
+        sV[j * Dp + dd] = __ldg(P.x + ((size_t)b * P.n + j0 + j) * P.k + dd);
+      }
+    }
+    __syncthreads();
+    // micro tile 2 x 2 over (i, j)
+    const int ntj = (jt + 1) >> 1, nmt = ((rb + 1) >> 1) * ntj;
+    for (int mt = tid; mt < nmt; mt += nth) {
+      int ti = mt / ntj, tj = mt - ti * ntj;
+      int ia = ti * 2, ib = min(ia + 1, rb - 1), ja = tj * 2, jb = min(ja + 1, jt - 1);
+      const float* s0 = sdS + ia * Dp; const float* s1 = sdS + ib * Dp;
+      const float* v0 = sV + ja * Dp; const float* v1 = sV + jb * Dp;
+      float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
+      for (int dd = 0; dd < D; ++dd) {
+        float x0 = s0[dd], x1 = s1[dd], y0 = v0[dd], y1 = v1[dd];
+        a00 = fmaf(x0, y0, a00); a01 = fmaf(x0, y1, a01); a10 = fmaf(x1, y0, a10); a11 = fmaf(x1, y1, a11);
+      }
+      sD[ia * Kp + j0 + ja] = a00;
+      if (ja + 1 < jt) sD[ia * Kp + j0 + ja + 1] = a01;
+      if (ia + 1 < rb) {
+        sD[(ia + 1) * Kp + j0 + ja] = a10;
+        if (ja + 1 < jt) sD[(ia + 1) * Kp + j0 + ja + 1] = a11;
+      }
+    }
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+  for (int i = warp; i < rb; i += nw) {
+    const float* arow = P.att + ((size_t)b * K + i0 + i) * Kp;
+    float* drow = sD + i * Kp;
+    float dot = 0.f;
+    for (int j = lane; j < K; j += 32) {
+      float da = drow[j];
+      if (P.p > 0.f) da *= dropout_mult(P.seed, P.stream, ((unsigned long long)b * K + i0 + i) * K + j, P.p, P.inv_keep);
+      drow[j] = da;
+      dot += __ldg(arow + j) * da;
+    }
+    dot = warp_sum(dot);
+    float* erow = P.de + ((size_t)b * K + i0 + i) * Kp;
+    for (int j = lane; j < Kp; j += 32) erow[j] = (j < K) ? __ldg(arow + j) * (drow[j] - dot) : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward 2: dX[r][d] = sign_d * sum_c w(r,c) [X_rd + Y_cd > 0]  for X in {P (pass 0), Q (pass 1)},
+// plus the rank-1 channel  dx1[r] = sum_c w(r,c) * (v2 ? alpha : lrelu'(x1_r + y1_c)).
+//   pass 0: r = i, c = j, w(r,c) = de[i][j]      pass 1: r = j, c = i, w(r,c) = de[i][j]
+// grid: (channel tiles, 1, B); the rank-1 channel is handled by channel-tile 0.
+// ---------------------------------------------------------------------------------------------
+struct Bwd2Params {
+  const float* pqt; const float* de; const int* meta; float* dpqt;
+  int K, Kp, E, NC, DT, v2, pass; float alpha;
+};
+
+__global__ void __launch_bounds__(256) gat_bwd2_kernel(Bwd2Params P) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.z, d0 = blockIdx.x * P.DT;
+  const int K = P.K, Kp = P.Kp, E = P.E;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  float* sW = smem;                         // [K (c)][Kp (r)]
+  float* sY = sW + (size_t)K * Kp;          // [DT+1][Kp]  (row DT = rank-1 channel of Y)
+  const float* pq = P.pqt + (size_t)b * P.NC * Kp;
+  const float* de = P.de + (size_t)b * K * Kp;
+  const int xoff = P.pass ? E : 0, yoff = P.pass ? 0 : E;
+  const int x1 = 2 * E + P.pass, y1 = 2 * E + 1 - P.pass;
+  const int dt = max(0, min(P.DT, E - d0));
+  // stage w as [c][r]
+  if (P.pass == 0) {
+    for (int idx = tid; idx < K * Kp; idx += nth) {
+      int r = idx / Kp, c = idx - r * Kp;     // coalesced read of de[r][c]
+      if (c < K) sW[c * Kp + r] = de[r * Kp + c];
+    }
+    // zero the pad columns r in [K,Kp)
+    for (int idx = tid; idx < K * (Kp - K); idx += nth) {
+      int c = idx / (Kp - K), r = K + idx - c * (Kp - K);
+      sW[c * Kp + r] = 0.f;
+    }
+  } else {
+    for (int idx = tid; idx < K * Kp; idx += nth) sW[idx] = de[idx];   // c = i rows, r = j columns
+  }
+  for (int idx = tid; idx < dt * Kp; idx += nth) {
+    int d = idx / Kp, c = idx - d * Kp;
+    sY[idx] = pq[(size_t)(yoff + d0 + d) * Kp + c];
+  }
+  for (int c = tid; c < Kp; c += nth) sY[P.DT * Kp + c] = pq[(size_t)y1 * Kp + c];
+  __syncthreads();
+  const int npos = P.v2 ? P.meta[0] : 0;
+  const int nrg = Kp >> 2;
+  const int nitems = nrg * dt;
+  float* dpq = P.dpqt + (size_t)b * P.NC * Kp;
+  for (int it = tid; it < nitems; it += nth) {
+    int d = it / nrg, rg = it - d * nrg;
+    float4 xv = *reinterpret_cast<const float4*>(pq + (size_t)(xoff + d0 + d) * Kp + rg * 4);
+    const float* yrow = sY + d * Kp;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int c = 0; c < K; ++c) {
+      float y = yrow[c];
+      float4 w = *reinterpret_cast<const float4*>(sW + c * Kp + rg * 4);
+      a0 += (xv.x + y > 0.f) ? w.x : 0.f;
+      a1 += (xv.y + y > 0.f) ? w.y : 0.f;
+      a2 += (xv.z + y > 0.f) ? w.z : 0.f;
+      a3 += (xv.w + y > 0.f) ? w.w : 0.f;
+    }
+    float sg = (d0 + d < npos) ? 1.f : -1.f;
+    *reinterpret_cast<float4*>(dpq + (size_t)(xoff + d0 + d) * Kp + rg * 4) = make_float4(sg * a0, sg * a1, sg * a2, sg * a3);
+  }
+  if (blockIdx.x == 0) {
+    const float* yrow = sY + P.DT * Kp;
+    for (int r = tid; r < Kp; r += nth) {
+      float acc = 0.f;
+      if (r < K) {
+        float xr = pq[(size_t)x1 * Kp + r];
+        for (int c = 0; c < K; ++c) {
+          float w = sW[c * Kp + r];
+          float g = P.v2 ? P.alpha : ((xr + yrow[c] > 0.f) ? 1.f : P.alpha);
+          acc = fmaf(w, g, acc);
+        }
+      }
+      dpq[(size_t)x1 * Kp + r] = acc;
+    }
+  }
+}
+
+static int pick_score_tiles(const GatDims& d, int& RB, int& JT, int& DT, size_t& smem) {
+  const size_t budget = 200 * 1024;
+  // rows per CTA: the aggregation gives each thread one 4x4 (i,dd) tile -> RB <= 4*floor(256/ceil(D/4))
+  int ntd = (d.D + 3) / 4;
+  if (ntd > 256) return -1;
+  int rbmax = 4 * (256 / ntd);
+  RB = min(d.K, rbmax);
+  // keep roughly >= 2 CTAs per window when K is large enough so small batches still fill the GPU
+  if (d.K >= 64) RB = min(RB, (d.K + 1) / 2);
+  JT = d.K; DT = d.E > 0 ? d.E : 1;
+  for (;;) {
+    int RBp = (RB + 3) & ~3, JTp = (JT + 3) & ~3;
+    size_t tiles = (size_t)DT * RBp + (size_t)DT * JTp;
+    size_t vt = (size_t)JT * (d.D + 1);
+    smem = sizeof(float) * ((size_t)RB * d.Kp + max(tiles, vt));
+    if (smem <= budget) return 0;
+    if (DT > 32) DT = (DT + 1) / 2;
+    else if (JT > 32) JT = (JT + 1) / 2;
+    else if (RB > 4) RB = (RB + 1) / 2;
+    else return -1;
+  }
+}
+
+template <int MI, int MJ>
+static void launch_score(const ScoreParams& P, dim3 grid, size_t smem, cudaStream_t s) {
+  cudaFuncSetAttribute(gat_score_fwd_kernel<MI, MJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  gat_score_fwd_kernel<MI, MJ><<<grid, 256, smem, s>>>(P);
+  MG_COUNT_LAUNCH();
+}
+
+}  // namespace
+
+extern "C" long long mtadgat_gat_saved_floats(int B, int n, int k, int E, int feature, int use_gatv2, int training) {
+  GatDims d = make_dims(B, n, k, E, feature, use_gatv2);
+  return (long long)saved_layout(d, E, training).total;
+}
+
+extern "C" long long mtadgat_gat_bwd_scratch_floats(int B, int n, int k, int E, int feature, int use_gatv2) {
+  GatDims d = make_dims(B, n, k, E, feature, use_gatv2);
+  // ds (B,K,D) | de (B,K,Kp) | dpqt (B,NC,Kp) | dwp (D,NC) | dbp (NC)
+  return (long long)((size_t)d.B * d.K * d.D + (size_t)d.B * d.K * d.Kp + (size_t)d.B * d.NC * d.Kp +
+                     (size_t)d.D * d.NC + d.NC + 16);
+}
+
+extern "C" int mtadgat_gat_fwd(const float* x, const float* lin_w, const float* lin_b, const float* a,
+                               const float* bias, float* out, float* saved, int B, int n, int k, int E, int feature,
+                               int use_gatv2, float alpha, int training, float p_drop,
+                               const unsigned long long* seed, void* stream) {
+  MG_CHECK_ARG(x && lin_w && lin_b && a && out && saved, "gat_fwd: null pointer");
+  MG_CHECK_ARG(B > 0 && n > 0 && k > 0 && E > 0, "gat_fwd: bad shape");
+  MG_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "gat_fwd: dropout p must be in [0,1)");
+  MG_CHECK_ARG(!(training && p_drop > 0.f) || seed, "gat_fwd: dropout needs a seed pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  GatDims d = make_dims(B, n, k, E, feature, use_gatv2);
+  SavedLayout L = saved_layout(d, E, training);
+  float* wp = saved + L.wp; float* bp = saved + L.bp; int* meta = reinterpret_cast<int*>(saved + L.meta);
+  float* pqt = saved + L.pqt; float* att = training ? saved + L.att : nullptr;
+  if (use_gatv2) { gat_prep_perm_kernel<<<1, 32, 0, s>>>(a, E, meta); MG_COUNT_LAUNCH(); }
+  {
+    int total = (d.D + 1) * d.NC;
+    gat_prep_fill_kernel<<<cdiv(total, 256), 256, 0, s>>>(lin_w, lin_b, a, meta, alpha, d.D, E, use_gatv2, wp, bp);
+    MG_COUNT_LAUNCH();
+  }
+  {
+    WpT A{wp, d.NC};
+    StPQt C{pqt, bp, d.NC, d.Kp};
+    if (feature) launch_gemm_batched(B, d.NC, d.K, d.D, A, NodeB<true>{x, n, k}, C, s);
+    else launch_gemm_batched(B, d.NC, d.K, d.D, A, NodeB<false>{x, n, k}, C, s);
+  }
+  int RB, JT, DT; size_t smem;
+  MG_CHECK_ARG(pick_score_tiles(d, RB, JT, DT, smem) == 0, "gat_fwd: shape outside the kernel envelope (D=%d)", d.D);
+  ScoreParams P;
+  P.x = x; P.pqt = pqt; P.bias = bias; P.meta = meta; P.out = out; P.att = att;
+  P.n = n; P.k = k; P.K = d.K; P.D = d.D; P.E = d.E; P.NC = d.NC; P.Kp = d.Kp;
+  P.RB = RB; P.JT = JT; P.DT = DT; P.feature = feature; P.v2 = use_gatv2; P.alpha = alpha;
+  P.p = training ? p_drop : 0.f; P.inv_keep = 1.f / (1.f - P.p); P.seed = seed; P.stream = feature ? 1u : 2u;
+  dim3 grid(cdiv(d.K, RB), B);
+  // micro-tile choice: keep most of the 256 threads busy for small K
+  long long mt44 = (long long)cdiv(RB, 4) * cdiv(min(JT, d.K), 4);
+  if (mt44 >= 200) launch_score<4, 4>(P, grid, smem, s);
+  else if ((long long)cdiv(RB, 2) * cdiv(min(JT, d.K), 4) >= 160) launch_score<2, 4>(P, grid, smem, s);
+  else launch_score<2, 2>(P, grid, smem, s);
+  MG_CHECK_LAUNCH("gat_fwd");
+  return MTADGAT_OK;
+}
+
+extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* lin_b, const float* a,
+                               const float* out, const float* gout, const float* saved, float* scratch, float* dx,
+                               int dx_accumulate, float* dlin_w, float* dlin_b, float* da, float* dbias, int B, int n,
+                               int k, int E, int feature, int use_gatv2, float alpha, float p_drop,
+                               const unsigned long long* seed, void* stream) {
+  MG_CHECK_ARG(x && lin_w && lin_b && a && out && gout && saved && scratch && dx && dlin_w && dlin_b && da,
+               "gat_bwd: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  GatDims d = make_dims(B, n, k, E, feature, use_gatv2);
+  SavedLayout L = saved_layout(d, E, 1);
+  const float* wp = saved + L.wp; const int* meta = reinterpret_cast<const int*>(saved + L.meta);
+  const float* pqt = saved + L.pqt; const float* att = saved + L.att;
+  float* ds = scratch;
+  float* de = ds + (size_t)d.B * d.K * d.D;
+  float* dpqt = de + (size_t)d.B * d.K * d.Kp;
+  float* dwp = dpqt + (size_t)d.B * d.NC * d.Kp;
+  float* dbp = dwp + (size_t)d.D * d.NC;
+  const float inv_keep = 1.f / (1.f - p_drop);
+  const uint32_t strm = feature ? 1u : 2u;
+  // ---- bwd1 ----
+  {
+    int RB = min(d.K, 64), JT = min(d.K, 64);
+    size_t smem;
+    for (;;) {
+      smem = sizeof(float) * ((size_t)RB * d.Kp + (size_t)RB * (d.D + 1) + (size_t)JT * (d.D + 1));
+      if (smem <= 200 * 1024) break;
+      if (JT > 8) JT = (JT + 1) / 2;
+      else if (RB > 1) RB = (RB + 1) / 2;
+      else { mtadgat_set_error("gat_bwd: shape outside the kernel envelope"); return MTADGAT_ERR_UNSUPPORTED; }
+    }
+    Bwd1Params P;
+    P.x = x; P.out = out; P.gout = gout; P.att = att; P.ds = ds; P.de = de;
+    P.n = n; P.k = k; P.K = d.K; P.D = d.D; P.Kp = d.Kp; P.RB = RB; P.JT = JT; P.feature = feature;
+    P.p = p_drop; P.inv_keep = inv_keep; P.seed = seed; P.stream = strm;
+    cudaFuncSetAttribute(gat_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gat_bwd1_kernel<<<dim3(cdiv(d.K, RB), B), 256, smem, s>>>(P);
+    MG_COUNT_LAUNCH();
+  }
+  // ---- dbias ----
+  if (dbias) {
+    MG_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)d.K * d.K, s));
+    launch_colsum(B, d.K * d.K, DeCols{de, d.K, d.Kp}, dbias, s);
+  }
+  // ---- bwd2 (two passes) ----
+  {
+    int DT = d.E > 0 ? d.E : 1;
+    size_t smem;
+    for (;;) {
+      smem = sizeof(float) * ((size_t)d.K * d.Kp + (size_t)(DT + 1) * d.Kp);
+      if (smem <= 200 * 1024 || DT <= 8) break;
+      DT = (DT + 1) / 2;
+    }
+    // more CTAs when the batch is small: split channels further
+    while ((long long)cdiv(max(d.E, 1), DT) * B < 296 && DT > 16) DT = (DT + 1) / 2;
+    smem = sizeof(float) * ((size_t)d.K * d.Kp + (size_t)(DT + 1) * d.Kp);
+    MG_CHECK_ARG(smem <= 220 * 1024, "gat_bwd: K=%d too large for the de tile", d.K);
+    cudaFuncSetAttribute(gat_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int pass = 0; pass < 2; ++pass) {
+      Bwd2Params P;
+      P.pqt = pqt; P.de = de; P.meta = meta; P.dpqt = dpqt; P.K = d.K; P.Kp = d.Kp; P.E = d.E; P.NC = d.NC;
+      P.DT = DT; P.v2 = use_gatv2; P.pass = pass; P.alpha = alpha;
+      gat_bwd2_kernel<<<dim3(max(1, cdiv(d.E, DT)), 1, B), 256, smem, s>>>(P);
+      MG_COUNT_LAUNCH();
+    }
+  }
+  // ---- weight-side GEMMs ----
+  MG_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * ((size_t)d.D * d.NC + d.NC), s));
+  {
+    DpqB Bq{dpqt, d.NC, d.Kp, d.K};
+    StAtomic2 C{dwp, d.NC};
+    if (feature) launch_gemm_splitk(d.D, d.NC, B * d.K, NodeAT<true>{x, n, k, d.K}, Bq, C, s);
+    else launch_gemm_splitk(d.D, d.NC, B * d.K, NodeAT<false>{x, n, k, d.K}, Bq, C, s);
+    launch_colsum(B * d.K, d.NC, DpqCols{dpqt, d.NC, d.Kp, d.K}, dbp, s);
+  }
+  {
+    int nw = 8;
+    gat_prep_bwd_kernel<<<cdiv(E, nw), nw * 32, 0, s>>>(lin_w, lin_b, a, meta, alpha, d.D, E, use_gatv2, dwp, dbp,
+                                                        dlin_w, dlin_b, da);
+    MG_COUNT_LAUNCH();
+  }
+  // ---- data gradient: dV = A~^T dS + dPQ Wp^T ----
+  {
+    AttTA A{att, d.K, d.Kp, p_drop, inv_keep, seed, strm};
+    DsB Bd{ds, d.K, d.D};
+    if (feature) launch_gemm_batched(B, d.K, d.D, d.K, A, Bd, StNodeAcc<true>{dx, n, k, dx_accumulate}, s);
+    else launch_gemm_batched(B, d.K, d.D, d.K, A, Bd, StNodeAcc<false>{dx, n, k, dx_accumulate}, s);
+    DpqA A2{dpqt, d.NC, d.Kp};
+    WpB B2{wp, d.NC};
+    if (feature) launch_gemm_batched(B, d.K, d.D, d.NC, A2, B2, StNodeAcc<true>{dx, n, k, 1}, s);
+    else launch_gemm_batched(B, d.K, d.D, d.NC, A2, B2, StNodeAcc<false>{dx, n, k, 1}, s);
+  }
+  MG_CHECK_LAUNCH("gat_bwd");
+  return MTADGAT_OK;
+}

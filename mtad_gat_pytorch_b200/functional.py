@@ -1,0 +1,257 @@
+"""torch.autograd bridges onto the C ABI (include/mtadgat.h).
+
+PyTorch is used here only as plumbing: device memory (caching allocator), the current CUDA stream, and the
+autograd tape.  All arithmetic happens in libmtadgat.so.  Inputs must be CUDA tensors -- there is no CPU path.
+"""
+import torch
+
+from ._lib import lib, check, MtadGatLibraryError
+
+RNG_FEATURE, RNG_TEMPORAL, RNG_MLP0, RNG_GRU0 = 1, 2, 16, 64
+
+
+def _prep(t, name="tensor"):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise MtadGatLibraryError(
+            f"{name} is on {t.device}: mtad_gat_pytorch_b200 runs only on CUDA (sm_100a); there is no CPU fallback")
+    if t.dtype != torch.float32:
+        raise MtadGatLibraryError(f"{name} must be float32 (got {t.dtype})")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def require_cuda(t, name="tensor"):
+    if not t.is_cuda:
+        raise MtadGatLibraryError(
+            f"{name} is on {t.device}: mtad_gat_pytorch_b200 runs only on CUDA (sm_100a); there is no CPU fallback")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _empty(n, like):
+    return torch.empty(int(max(n, 1)), dtype=torch.float32, device=like.device)
+
+
+# ---------------------------------------------------------------------------------------------------
+# dropout seeds: one uint64 per device in HBM, advanced by a kernel (CUDA-graph replay safe)
+# ---------------------------------------------------------------------------------------------------
+_seed_state = {}
+
+
+def fresh_seed(device):
+    """Advance the per-device seed and return a private copy (kept by autograd for the backward)."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _seed_state.get(key)
+    if st is None:
+        st = torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+        _seed_state[key] = st
+    check(lib.mtadgat_seed_advance(st.data_ptr(), _stream()))
+    return st.clone()
+
+
+def manual_seed(seed, device=None):
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    _seed_state[key] = torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device=device)
+
+
+def dropout_multipliers(numel, p, seed_t, rng_stream):
+    """The multipliers (0 or 1/(1-p)) the kernels apply for (seed, stream); used by the tests."""
+    out = torch.empty(int(numel), dtype=torch.float32, device=seed_t.device)
+    check(lib.mtadgat_dropout_mask(out.data_ptr(), int(numel), float(p), seed_t.data_ptr(), int(rng_stream), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+class ConvReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w, b = _prep(x, "x"), _prep(w, "conv weight"), _prep(b, "conv bias")
+        B, n, k = x.shape
+        ks = w.shape[2]
+        y = torch.empty_like(x)
+        check(lib.mtadgat_conv_relu_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, n, k, ks, _stream()))
+        ctx.save_for_backward(x, w, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        dy = _prep(dy, "dy")
+        B, n, k = x.shape
+        ks = w.shape[2]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(k, dtype=torch.float32, device=x.device)
+        check(lib.mtadgat_conv_relu_bwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dx),
+                                        dw.data_ptr(), db.data_ptr(), B, n, k, ks, _stream()))
+        return dx, dw, db
+
+
+class GatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, lin_w, lin_b, a, bias, feature, use_gatv2, alpha, p_drop, seed_t):
+        x, lin_w, lin_b, a, bias = _prep(x, "x"), _prep(lin_w), _prep(lin_b), _prep(a), _prep(bias)
+        B, n, k = x.shape
+        E = lin_w.shape[0]
+        save = 1 if any(ctx.needs_input_grad) else 0
+        nsaved = lib.mtadgat_gat_saved_floats(B, n, k, E, int(feature), int(use_gatv2), save)
+        saved = _empty(nsaved, x)
+        out = torch.empty_like(x)
+        check(lib.mtadgat_gat_fwd(x.data_ptr(), lin_w.data_ptr(), lin_b.data_ptr(), a.data_ptr(), _ptr(bias),
+                                  out.data_ptr(), saved.data_ptr(), B, n, k, E, int(feature), int(use_gatv2),
+                                  float(alpha), save, float(p_drop), _ptr(seed_t), _stream()))
+        ctx.save_for_backward(x, lin_w, lin_b, a, out, saved, seed_t if seed_t is not None else torch.empty(0))
+        ctx.cfg = (int(feature), int(use_gatv2), float(alpha), float(p_drop), bias is not None, seed_t is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, lin_w, lin_b, a, out, saved, seed_t = ctx.saved_tensors
+        feature, v2, alpha, p, has_bias, has_seed = ctx.cfg
+        gout = _prep(gout, "grad")
+        B, n, k = x.shape
+        E = lin_w.shape[0]
+        K = k if feature else n
+        scratch = _empty(lib.mtadgat_gat_bwd_scratch_floats(B, n, k, E, feature, v2), x)
+        dx = torch.empty_like(x)
+        dw, db, da = torch.empty_like(lin_w), torch.empty_like(lin_b), torch.empty_like(a)
+        dbias = torch.empty(K, K, dtype=torch.float32, device=x.device) if has_bias else None
+        check(lib.mtadgat_gat_bwd(x.data_ptr(), lin_w.data_ptr(), lin_b.data_ptr(), a.data_ptr(), out.data_ptr(),
+                                  gout.data_ptr(), saved.data_ptr(), scratch.data_ptr(), dx.data_ptr(), 0,
+                                  dw.data_ptr(), db.data_ptr(), da.data_ptr(), _ptr(dbias), B, n, k, E, feature, v2,
+                                  alpha, p, seed_t.data_ptr() if has_seed else None, _stream()))
+        return dx, dw, db, da, dbias, None, None, None, None, None
+
+
+class GruFn(torch.autograd.Function):
+    """One GRU layer over the column-concatenation of up to three inputs; returns (out, h_last)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, x2, w_ih, w_hh, b_ih, b_hh, need_out):
+        ctx.set_materialize_grads(False)
+        xs = [_prep(t, "gru input") for t in (x0, x1, x2)]
+        w_ih, w_hh, b_ih, b_hh = _prep(w_ih), _prep(w_hh), _prep(b_ih), _prep(b_hh)
+        B, n = xs[0].shape[0], xs[0].shape[1]
+        ks = [0 if t is None else t.shape[2] for t in xs]
+        H = w_hh.shape[1]
+        save = 1 if any(ctx.needs_input_grad) else 0
+        dev = xs[0]
+        out = torch.empty(B, n, H, dtype=torch.float32, device=dev.device) if (save or need_out) else None
+        h_last = torch.empty(B, H, dtype=torch.float32, device=dev.device)
+        saved = _empty(lib.mtadgat_gru_saved_floats(B, n, H, save), dev)
+        scratch = _empty(lib.mtadgat_gru_fwd_scratch_floats(B, n, H), dev)
+        check(lib.mtadgat_gru_fwd(_ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), ks[0], ks[1], ks[2], w_ih.data_ptr(),
+                                  w_hh.data_ptr(), b_ih.data_ptr(), b_hh.data_ptr(), _ptr(out), h_last.data_ptr(),
+                                  saved.data_ptr(), scratch.data_ptr(), B, n, H, save, _stream()))
+        if save:
+            ctx.save_for_backward(*[t if t is not None else torch.empty(0) for t in xs], w_ih, w_hh, out, saved)
+            ctx.ks = ks
+        ret_out = out if out is not None else torch.empty(0, device=dev.device)
+        return ret_out, h_last
+
+    @staticmethod
+    def backward(ctx, dout, dh_last):
+        x0, x1, x2, w_ih, w_hh, out, saved = ctx.saved_tensors
+        ks = ctx.ks
+        B, n, H = out.shape
+        dout = _prep(dout) if dout is not None else None
+        dh_last = _prep(dh_last) if dh_last is not None else None
+        if dout is None and dh_last is None:
+            dh_last = torch.zeros(B, H, dtype=torch.float32, device=out.device)
+        scratch = _empty(lib.mtadgat_gru_bwd_scratch_floats(B, n, H), out)
+        xs = [x0, x1 if ks[1] else None, x2 if ks[2] else None]
+        dxs = [torch.empty_like(t) if (t is not None and ctx.needs_input_grad[i]) else None for i, t in enumerate(xs)]
+        dw_ih, dw_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
+        db_ih = torch.empty(3 * H, dtype=torch.float32, device=out.device)
+        db_hh = torch.empty_like(db_ih)
+        check(lib.mtadgat_gru_bwd(_ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), ks[0], ks[1], ks[2], w_ih.data_ptr(),
+                                  w_hh.data_ptr(), out.data_ptr(), saved.data_ptr(), _ptr(dout), _ptr(dh_last),
+                                  scratch.data_ptr(), _ptr(dxs[0]), _ptr(dxs[1]), _ptr(dxs[2]), 0, 0, 0,
+                                  dw_ih.data_ptr(), dw_hh.data_ptr(), db_ih.data_ptr(), db_hh.data_ptr(), B, n, H,
+                                  _stream()))
+        return dxs[0], dxs[1], dxs[2], dw_ih, dw_hh, db_ih, db_hh, None
+
+
+class GruRepFn(torch.autograd.Function):
+    """Decoder GRU layer 0 over the reference's scrambled repeat of h_src (modules.py:279)."""
+
+    @staticmethod
+    def forward(ctx, h_src, w_ih, w_hh, b_ih, b_hh, n):
+        h_src, w_ih, w_hh, b_ih, b_hh = _prep(h_src, "h_end"), _prep(w_ih), _prep(w_hh), _prep(b_ih), _prep(b_hh)
+        B, Hs = h_src.shape
+        R = w_hh.shape[1]
+        save = 1 if any(ctx.needs_input_grad) else 0
+        out = torch.empty(B, n, R, dtype=torch.float32, device=h_src.device)
+        saved = _empty(lib.mtadgat_gru_rep_saved_floats(B, n, Hs, R, save), h_src)
+        check(lib.mtadgat_gru_rep_fwd(h_src.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), b_ih.data_ptr(),
+                                      b_hh.data_ptr(), out.data_ptr(), saved.data_ptr(), B, n, Hs, R, save, _stream()))
+        if save:
+            ctx.save_for_backward(h_src, w_ih, w_hh, out, saved)
+        ctx.n = n
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h_src, w_ih, w_hh, out, saved = ctx.saved_tensors
+        n = ctx.n
+        dout = _prep(dout)
+        B, Hs = h_src.shape
+        R = w_hh.shape[1]
+        scratch = _empty(lib.mtadgat_gru_rep_bwd_scratch_floats(B, n, Hs, R), out)
+        dh = torch.empty_like(h_src)
+        dw_ih, dw_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
+        db_ih = torch.empty(3 * R, dtype=torch.float32, device=out.device)
+        db_hh = torch.empty_like(db_ih)
+        check(lib.mtadgat_gru_rep_bwd(h_src.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), out.data_ptr(),
+                                      saved.data_ptr(), dout.data_ptr(), scratch.data_ptr(), dh.data_ptr(), 0,
+                                      dw_ih.data_ptr(), dw_hh.data_ptr(), db_ih.data_ptr(), db_hh.data_ptr(), B, n,
+                                      Hs, R, _stream()))
+        return dh, dw_ih, dw_hh, db_ih, db_hh, None
+
+
+class LinearFn(torch.autograd.Function):
+    """y = dropout(act(x W^T + b)); x (..., I) is flattened to (M, I)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act, p_drop, seed_t, rng_stream):
+        x, w, b = _prep(x, "x"), _prep(w), _prep(b)
+        O, I = w.shape
+        lead = x.shape[:-1]
+        M = x.numel() // I
+        y = torch.empty(*lead, O, dtype=torch.float32, device=x.device)
+        check(lib.mtadgat_linear_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), M, I, O, int(act),
+                                     float(p_drop), _ptr(seed_t), int(rng_stream), _stream()))
+        ctx.save_for_backward(x, w, y, seed_t if seed_t is not None else torch.empty(0))
+        ctx.cfg = (int(act), float(p_drop), seed_t is not None, int(rng_stream))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y, seed_t = ctx.saved_tensors
+        act, p, has_seed, rng_stream = ctx.cfg
+        dy = _prep(dy)
+        O, I = w.shape
+        M = x.numel() // I
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(O, dtype=torch.float32, device=x.device)
+        check(lib.mtadgat_linear_bwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dx), 0,
+                                     dw.data_ptr(), db.data_ptr(), M, I, O, act, p,
+                                     seed_t.data_ptr() if has_seed else None, rng_stream, _stream()))
+        return dx, dw, db, None, None, None, None
+
+
+def launch_count():
+    return int(lib.mtadgat_launch_count())
+
+
+def reset_launch_count():
+    lib.mtadgat_reset_launch_count()

@@ -1,0 +1,80 @@
+"""Per-stage timing of the C-ABI entry points with CUDA events (used by bench.py for the roofline block).
+
+For each stage of the path the table gives the measured duration (median of `reps`, L2 flushed and the
+queue primed before each timed call), the algorithmic bytes / dense FLOPs per launch (SURVEY.md §8d per-window
+figures x batch) and the fraction of the measured HBM / tensor peak."""
+import torch
+
+from . import functional as F
+
+
+def _time(fn, flush, reps=7):
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def stage_rooflines(model, B, peaks, dev):
+    n, k = model.temporal_gat.window_size, model.temporal_gat.n_features
+    H = model.gru.hid_dim
+    R = model.recon_model.decoder.rnn.hidden_size
+    out_dim = model.recon_model.fc.out_features
+    ks = model.conv.conv.kernel_size[0]
+    Ef, Et = model.feature_gat.lin.weight.shape[0], model.temporal_gat.lin.weight.shape[0]
+    L = len(model.forecasting_model.layers) - 1
+    Fh = model.forecasting_model.layers[0].out_features
+    flush = torch.empty(1024 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    was_training = model.training
+    model.eval()                      # dropout off: the stage timings are mask-free kernels
+    x = torch.rand(B, n, k, device=dev)
+    rows = []
+
+    def add(name, fwd, inputs, bytes_f, flops_f, bound):
+        # forward (saving for backward) and backward through the autograd bridge = one C call each
+        outs = {}
+
+        def f():
+            outs["o"] = fwd()
+        ms_f = _time(f, flush)
+        o = outs["o"]
+        o_list = [t for t in (o if isinstance(o, (tuple, list)) else [o]) if t.requires_grad]
+        go = [torch.ones_like(t) for t in o_list]
+        ms_b = _time(lambda: torch.autograd.grad(o_list, inputs, go, retain_graph=True, allow_unused=True), flush)
+        for tag, ms, by, fl in (("fwd", ms_f, bytes_f, flops_f), ("bwd", ms_b, 1.5 * bytes_f, 2.0 * flops_f)):
+            if bound == "hbm":
+                ach, peak, unit = by / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
+            else:
+                ach, peak, unit = fl / (ms * 1e-3) / 1e12, peaks["bf16_tflops"], "TFLOP/s"
+            rows.append({"kernel": f"{name}_{tag}", "ms": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+                         "frac": ach / peak, "traffic": None, "alg_bytes": by, "dense_flops": fl})
+
+    xg = x.clone().requires_grad_(True)
+    conv_p = list(model.conv.parameters())
+    add("conv", lambda: model.conv(xg), [xg] + conv_p, 2 * n * k * 4 * B, 2 * n * k * k * ks * B, "hbm")
+    xc = model.conv(x).detach().requires_grad_(True)
+    fp, tp = list(model.feature_gat.parameters()), list(model.temporal_gat.parameters())
+    add("feat_gat", lambda: model.feature_gat(xc), [xc] + fp, 2 * n * k * 4 * B,
+        (2 * k * n * (Ef + 2) + 2 * k * k * n) * B, "hbm")
+    add("temp_gat", lambda: model.temporal_gat(xc), [xc] + tp, 2 * n * k * 4 * B,
+        (2 * n * k * (Et + 2) + 2 * n * n * k) * B, "hbm")
+    hf = model.feature_gat(xc).detach().requires_grad_(True)
+    ht = model.temporal_gat(xc).detach().requires_grad_(True)
+    gp = list(model.gru.parameters())
+    add("enc_gru", lambda: model.gru.forward_slices([xc, hf, ht]), [xc, hf, ht] + gp, (3 * n * k + H + n * H) * 4 * B,
+        (2 * n * 3 * k * 3 * H + 2 * n * H * 3 * H) * B, "tensor")
+    h_end = model.gru.forward_slices([xc, hf, ht]).detach().requires_grad_(True)
+    mp = list(model.forecasting_model.parameters())
+    add("mlp", lambda: model.forecasting_model(h_end), [h_end] + mp, (H + out_dim) * 4 * B,
+        2 * (H * Fh + (L - 1) * Fh * Fh + Fh * out_dim) * B, "tensor")
+    rp = list(model.recon_model.parameters())
+    add("recon", lambda: model.recon_model(h_end), [h_end] + rp, (H + n * out_dim) * 4 * B,
+        (2 * n * R * 3 * R + 2 * n * R * out_dim) * B, "tensor")
+    model.train(was_training)
+    del flush
+    return rows

@@ -1,0 +1,184 @@
+"""Host-side mirror of the reference's `modules.py` classes for the B200 hot path.
+
+Same class names, constructor signatures, parameter names/shapes (hence the same state-dict and, because the
+parameter containers are constructed in the same order with the same torch initialisers, the same values
+under the same torch seed) and forward signatures as the reference.  The `nn.Conv1d`,
+`nn.Linear` and `nn.GRU` members are used ONLY as parameter containers -- their forwards are never called;
+every forward/backward runs in libmtadgat.so through `functional.py`.  CUDA only: CPU tensors raise.
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as F
+
+
+class _SeedMixin:
+    """Dropout seed plumbing: MTAD_GAT hands one per-step seed to its children; a layer used on its own
+    draws a fresh one per call."""
+    _step_seed = None
+
+    def _seed(self, device, p):
+        if not (self.training and p > 0.0):
+            return None
+        return self._step_seed if self._step_seed is not None else F.fresh_seed(device)
+
+
+class ConvLayer(nn.Module):
+    """1-D convolution over time + ReLU (reference modules.py:5-22).  (B,n,k) -> (B,n,k)."""
+
+    def __init__(self, n_features, kernel_size=7):
+        super().__init__()
+        if kernel_size % 2 == 0:
+            raise ValueError("kernel_size must be odd: an even size changes the window length in the reference")
+        self.conv = nn.Conv1d(in_channels=n_features, out_channels=n_features, kernel_size=kernel_size)
+
+    def forward(self, x):
+        return F.ConvReluFn.apply(x, self.conv.weight, self.conv.bias)
+
+
+class _GraphAttention(nn.Module, _SeedMixin):
+    """Shared body of the feature- and time-oriented GAT layers (reference modules.py:25-217)."""
+    _feature = None
+
+    def __init__(self, n_features, window_size, dropout, alpha, embed_dim=None, use_gatv2=True, use_bias=True):
+        super().__init__()
+        self.n_features = n_features
+        self.window_size = window_size
+        self.dropout = dropout
+        self.alpha = alpha
+        self.use_gatv2 = use_gatv2
+        self.use_bias = use_bias
+        node_dim = window_size if self._feature else n_features     # length of one node's vector
+        self.num_nodes = n_features if self._feature else window_size
+        self.embed_dim = embed_dim if embed_dim is not None else node_dim
+        if use_gatv2:                       # linear map applied to the concatenated pair (modules.py:46-49)
+            self.embed_dim *= 2
+            lin_in, a_in = 2 * node_dim, self.embed_dim
+        else:
+            lin_in, a_in = node_dim, 2 * self.embed_dim
+        self.lin = nn.Linear(lin_in, self.embed_dim)
+        self.a = nn.Parameter(torch.empty((a_in, 1)))
+        nn.init.xavier_uniform_(self.a.data, gain=1.414)
+        if use_bias:
+            self.bias = nn.Parameter(torch.zeros(self.num_nodes, self.num_nodes))
+
+    def forward(self, x):
+        p = self.dropout if self.training else 0.0
+        return F.GatFn.apply(x, self.lin.weight, self.lin.bias, self.a, self.bias if self.use_bias else None,
+                             self._feature, self.use_gatv2, self.alpha, p, self._seed(x.device, p))
+
+
+class FeatureAttentionLayer(_GraphAttention):
+    """Nodes = the k features, node vector = its n values (reference modules.py:25-122)."""
+    _feature = True
+
+
+class TemporalAttentionLayer(_GraphAttention):
+    """Nodes = the n timestamps, node vector = its k feature values (reference modules.py:125-217)."""
+    _feature = False
+
+
+def _gru_stack(rnn, layer0, n_layers, p_between, training, seed_fn):
+    """Layers 1.. of an nn.GRU parameter container on top of `layer0`'s per-step outputs."""
+    out, h_last = layer0
+    for l in range(1, n_layers):
+        if training and p_between > 0.0:     # nn.GRU inter-layer dropout (modules.py:231-233)
+            m = F.dropout_multipliers(out.numel(), p_between, seed_fn(), F.RNG_GRU0 + l).view_as(out)
+            out = out * m
+        out, h_last = F.GruFn.apply(out, None, None, getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}"),
+                                    getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}"), True)
+    return out, h_last
+
+
+class GRULayer(nn.Module, _SeedMixin):
+    """Encoder GRU (reference modules.py:220-238)."""
+
+    def __init__(self, in_dim, hid_dim, n_layers, dropout):
+        super().__init__()
+        self.hid_dim = hid_dim
+        self.n_layers = n_layers
+        self.dropout = 0.0 if n_layers == 1 else dropout
+        self.gru = nn.GRU(in_dim, hid_dim, num_layers=n_layers, batch_first=True, dropout=self.dropout)
+
+    def _run(self, slices, need_out):
+        g = self.gru
+        xs = list(slices) + [None] * (3 - len(slices))
+        multi = self.n_layers > 1
+        layer0 = F.GruFn.apply(xs[0], xs[1], xs[2], g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0,
+                               need_out or multi)
+        if multi:
+            dev = xs[0].device
+            return _gru_stack(g, layer0, self.n_layers, self.dropout, self.training,
+                              lambda: self._step_seed if self._step_seed is not None else F.fresh_seed(dev))
+        return layer0
+
+    def forward_slices(self, slices):
+        """h_n[-1] (B,H) of the GRU run over torch.cat(slices, dim=2) without materialising the cat
+        (what MTAD_GAT.forward consumes, mtad_gat.py:71-74)."""
+        return self._run(slices, need_out=False)[1]
+
+    def forward(self, x):
+        out, h = self._run([x], need_out=True)
+        return out[-1, :, :], h               # the reference returns out[-1]: the last *batch element* (modules.py:237)
+
+
+class RNNDecoder(nn.Module, _SeedMixin):
+    """Decoder GRU (reference modules.py:241-257): all n outputs."""
+
+    def __init__(self, in_dim, hid_dim, n_layers, dropout):
+        super().__init__()
+        self.in_dim = in_dim
+        self.n_layers = n_layers
+        self.dropout = 0.0 if n_layers == 1 else dropout
+        self.rnn = nn.GRU(in_dim, hid_dim, n_layers, batch_first=True, dropout=self.dropout)
+
+    def _finish(self, out, dev):
+        if self.n_layers == 1:
+            return out
+        return _gru_stack(self.rnn, (out, None), self.n_layers, self.dropout, self.training,
+                          lambda: self._step_seed if self._step_seed is not None else F.fresh_seed(dev))[0]
+
+    def forward_repeat(self, h_end, window_size):
+        """Decoder over the reference's scrambled repeat of h_end (modules.py:279) without building it."""
+        r = self.rnn
+        out = F.GruRepFn.apply(h_end, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, int(window_size))
+        return self._finish(out, h_end.device)
+
+    def forward(self, x):
+        r = self.rnn
+        out, _ = F.GruFn.apply(x, None, None, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, True)
+        return self._finish(out, x.device)
+
+
+class ReconstructionModel(nn.Module):
+    """GRU decoder + Linear (reference modules.py:260-283)."""
+
+    def __init__(self, window_size, in_dim, hid_dim, out_dim, n_layers, dropout):
+        super().__init__()
+        self.window_size = window_size
+        self.decoder = RNNDecoder(in_dim, hid_dim, n_layers, dropout)
+        self.fc = nn.Linear(hid_dim, out_dim)
+
+    def forward(self, x):
+        dec = self.decoder.forward_repeat(x, self.window_size)
+        return F.LinearFn.apply(dec, self.fc.weight, self.fc.bias, 0, 0.0, None, 0)
+
+
+class Forecasting_Model(nn.Module, _SeedMixin):
+    """n_layers+1 Linear layers, ReLU+Dropout after all but the last (reference modules.py:286-311)."""
+
+    def __init__(self, in_dim, hid_dim, out_dim, n_layers, dropout):
+        super().__init__()
+        layers = [nn.Linear(in_dim, hid_dim)]
+        for _ in range(n_layers - 1):
+            layers.append(nn.Linear(hid_dim, hid_dim))
+        layers.append(nn.Linear(hid_dim, out_dim))
+        self.layers = nn.ModuleList(layers)
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, x):
+        p = self.dropout.p if self.training else 0.0
+        seed = self._seed(x.device, p)
+        for i in range(len(self.layers) - 1):
+            x = F.LinearFn.apply(x, self.layers[i].weight, self.layers[i].bias, 1, p, seed, F.RNG_MLP0 + i)
+        return F.LinearFn.apply(x, self.layers[-1].weight, self.layers[-1].bias, 0, 0.0, None, 0)

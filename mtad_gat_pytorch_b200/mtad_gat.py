@@ -1,0 +1,45 @@
+"""`MTAD_GAT` with the reference's constructor / forward signature (reference mtad_gat.py:37-79), running the
+per-window pipeline on the sm_100a kernels in libmtadgat.so."""
+import torch.nn as nn
+
+from . import functional as F
+from .modules import (ConvLayer, FeatureAttentionLayer, TemporalAttentionLayer, GRULayer, Forecasting_Model,
+                      ReconstructionModel)
+
+
+class MTAD_GAT(nn.Module):
+    """x (B, n, k) float32 CUDA  ->  (predictions (B, out_dim), recons (B, n, out_dim)).
+
+    Arguments are the reference's (mtad_gat.py:37-54), positionally compatible with train.py:74-90."""
+
+    def __init__(self, n_features, window_size, out_dim, kernel_size=7, feat_gat_embed_dim=None,
+                 time_gat_embed_dim=None, use_gatv2=True, gru_n_layers=1, gru_hid_dim=150, forecast_n_layers=1,
+                 forecast_hid_dim=150, recon_n_layers=1, recon_hid_dim=150, dropout=0.2, alpha=0.2):
+        super().__init__()
+        self.conv = ConvLayer(n_features, kernel_size)
+        self.feature_gat = FeatureAttentionLayer(n_features, window_size, dropout, alpha, feat_gat_embed_dim, use_gatv2)
+        self.temporal_gat = TemporalAttentionLayer(n_features, window_size, dropout, alpha, time_gat_embed_dim, use_gatv2)
+        self.gru = GRULayer(3 * n_features, gru_hid_dim, gru_n_layers, dropout)
+        self.forecasting_model = Forecasting_Model(gru_hid_dim, forecast_hid_dim, out_dim, forecast_n_layers, dropout)
+        self.recon_model = ReconstructionModel(window_size, gru_hid_dim, recon_hid_dim, out_dim, recon_n_layers, dropout)
+        self._dropout = dropout
+
+    def _seeded(self):
+        return (self.feature_gat, self.temporal_gat, self.gru, self.forecasting_model, self.recon_model.decoder)
+
+    def forward(self, x):
+        F.require_cuda(x, "MTAD_GAT input")
+        seed = F.fresh_seed(x.device) if (self.training and self._dropout > 0.0) else None
+        for m in self._seeded():
+            m._step_seed = seed
+        try:
+            xc = self.conv(x)                                   # mtad_gat.py:67
+            h_feat = self.feature_gat(xc)                       # :68
+            h_temp = self.temporal_gat(xc)                      # :69
+            h_end = self.gru.forward_slices([xc, h_feat, h_temp])   # :71-74 (cat never materialised)
+            predictions = self.forecasting_model(h_end)         # :76
+            recons = self.recon_model(h_end)                    # :77
+        finally:
+            for m in self._seeded():
+                m._step_seed = None
+        return predictions, recons
