@@ -88,6 +88,13 @@ int mtadgat_linear_bwd(const float* x, const float* w, const float* y, const flo
                        int dx_accumulate, float* dw, float* db, int M, int I, int O, int act, float p_drop,
                        const unsigned long long* seed, unsigned int rng_stream, void* stream);
 
+/* ---- recurrence implementation: 1 (default) = persistent tcgen05/TMEM kernel, fp16 operands with fp32
+ *      accumulation and fp32 hidden state (hidden sizes 8..256); 0 = fp32 SIMT kernel.  mtadgat_tc_probe runs one
+ *      128 x N x K product through the same shared-memory operand layout (diagnostic / unit test). ---- */
+int mtadgat_set_gru_impl(int impl);
+int mtadgat_get_gru_impl(void);
+int mtadgat_tc_probe(const float* A, const float* Bm, float* D, int Mtot, int row0, int K, int N, void* stream);
+
 /* ---- RNG plumbing ---- */
 int mtadgat_dropout_mask(float* out, long long numel, float p, const unsigned long long* seed,
                          unsigned int rng_stream, void* stream);   /* multipliers 0 or 1/(1-p), for tests */

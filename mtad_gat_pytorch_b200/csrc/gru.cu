@@ -9,6 +9,17 @@
 #include "gemm.cuh"
 #include "../../include/mtadgat.h"
 
+// tensor-core recurrence (gru_tc.cu)
+int mtadgat_gru_tc_supported(int H);
+int mtadgat_gru_tc_fwd_launch(const float* gi, const float* S, const float* hsrc, const float* b_ih, int J, int Hs,
+                              const float* w_hh, const float* b_hh, float* out, float* h_last, float* gates, int B,
+                              int n, int H, cudaStream_t s);
+int mtadgat_gru_tc_bwd_supported(int H);
+int mtadgat_gru_tc_bwd_launch(const float* gates, const float* out, const float* w_hh, const float* dout,
+                              const float* dh_last, unsigned int* gmax_bits, float* dgi, float* dghn, int B, int n,
+                              int H, cudaStream_t s);
+static int g_gru_impl = 1;   // 0 = fp32 SIMT recurrence, 1 = tcgen05 fp16-operand recurrence (fp32 accumulate/state)
+
 namespace {
 
 constexpr int BT = 8;   // windows per CTA in the recurrent kernels
@@ -352,12 +363,19 @@ static void launch_transpose(const float* src, float* dst, int R, int C, cudaStr
 
 }  // namespace
 
+extern "C" int mtadgat_set_gru_impl(int impl) {
+  MG_CHECK_ARG(impl == 0 || impl == 1, "set_gru_impl: 0 (fp32 SIMT) or 1 (tcgen05)");
+  g_gru_impl = impl;
+  return MTADGAT_OK;
+}
+extern "C" int mtadgat_get_gru_impl(void) { return g_gru_impl; }
+
 // saved (floats): wt (H*3H) | gates (B*n*4H, only if save) ; gi scratch is separate
 extern "C" long long mtadgat_gru_saved_floats(int B, int n, int H, int save) {
   return (long long)((size_t)3 * H * H + (save ? (size_t)B * n * 4 * H : 0));
 }
 extern "C" long long mtadgat_gru_fwd_scratch_floats(int B, int n, int H) { return (long long)((size_t)B * n * 3 * H); }
-extern "C" long long mtadgat_gru_bwd_scratch_floats(int B, int n, int H) { return (long long)((size_t)B * n * 4 * H); }
+extern "C" long long mtadgat_gru_bwd_scratch_floats(int B, int n, int H) { return (long long)((size_t)B * n * 4 * H + 4); }
 
 extern "C" int mtadgat_gru_fwd(const float* x0, const float* x1, const float* x2, int k0, int k1, int k2,
                                const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
@@ -371,9 +389,14 @@ extern "C" int mtadgat_gru_fwd(const float* x0, const float* x1, const float* x2
   const int I = k0 + k1 + k2, G = 3 * H;
   float* wt = saved; float* gates = save ? saved + (size_t)3 * H * H : nullptr;
   float* gi = scratch;
-  launch_transpose(w_hh, wt, G, H, s);
   launch_gemm_batched(1, B * n, G, I, Cat3A{x0, x1, x2, k0, k1, k2}, WT{w_ih, I},
                       StStrided{gi, 0, G, 1, b_ih, ACT_NONE, 0}, s);
+  if (g_gru_impl == 1 && mtadgat_gru_tc_supported(H)) {
+    mtadgat_gru_tc_fwd_launch(gi, nullptr, nullptr, nullptr, 0, 0, w_hh, b_hh, out, h_last, gates, B, n, H, s);
+    MG_CHECK_LAUNCH("gru_fwd(tc)");
+    return MTADGAT_OK;
+  }
+  launch_transpose(w_hh, wt, G, H, s);
   GruFwdParams P;
   P.gi = gi; P.S = nullptr; P.hsrc = nullptr; P.b_ih = nullptr; P.J = 0; P.Hs = 0; P.wt = wt; P.b_hh = b_hh;
   P.out = out; P.h_last = h_last; P.gates = gates; P.B = B; P.n = n; P.H = H;
@@ -397,8 +420,13 @@ extern "C" int mtadgat_gru_bwd(const float* x0, const float* x1, const float* x2
   GruBwdParams P;
   P.gates = gates; P.out = out; P.w_hh = w_hh; P.dout = dout; P.dh_last = dh_last; P.dgi = dgi; P.dghn = dghn;
   P.B = B; P.n = n; P.H = H;
-  int rc = launch_gru_bwd(P, s);
-  if (rc) return rc;
+  if (g_gru_impl == 1 && mtadgat_gru_tc_bwd_supported(H)) {
+    unsigned int* gmax = reinterpret_cast<unsigned int*>(scratch + (size_t)B * n * 4 * H);
+    mtadgat_gru_tc_bwd_launch(gates, out, w_hh, dout, dh_last, gmax, dgi, dghn, B, n, H, s);
+  } else {
+    int rc = launch_gru_bwd(P, s);
+    if (rc) return rc;
+  }
   MG_CUDA(cudaMemsetAsync(dw_ih, 0, sizeof(float) * (size_t)G * I, s));
   MG_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * (size_t)G * H, s));
   MG_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)G, s));
@@ -426,7 +454,7 @@ extern "C" long long mtadgat_gru_rep_saved_floats(int B, int n, int Hs, int R, i
 // scratch for bwd: dgi (B*n*3R) | dghn (B*n*R) | dS (n*J*3R)
 extern "C" long long mtadgat_gru_rep_bwd_scratch_floats(int B, int n, int Hs, int R) {
   int J = rep_J(n, Hs);
-  return (long long)((size_t)B * n * 4 * R + (size_t)n * J * 3 * R);
+  return (long long)((size_t)B * n * 4 * R + (size_t)n * J * 3 * R + 4);
 }
 
 extern "C" int mtadgat_gru_rep_fwd(const float* h_src, const float* w_ih, const float* w_hh, const float* b_ih,
@@ -438,9 +466,14 @@ extern "C" int mtadgat_gru_rep_fwd(const float* h_src, const float* w_ih, const 
   const int G = 3 * R, J = rep_J(n, Hs);
   float* wt = saved; float* S = saved + (size_t)3 * R * R;
   float* gates = save ? S + (size_t)n * J * G : nullptr;
-  launch_transpose(w_hh, wt, G, R, s);
   rep_build_S_kernel<<<cdiv((long long)n * J * G, 256), 256, 0, s>>>(w_ih, n, Hs, G, J, S);
   MG_COUNT_LAUNCH();
+  if (g_gru_impl == 1 && mtadgat_gru_tc_supported(R)) {
+    mtadgat_gru_tc_fwd_launch(nullptr, S, h_src, b_ih, J, Hs, w_hh, b_hh, out, nullptr, gates, B, n, R, s);
+    MG_CHECK_LAUNCH("gru_rep_fwd(tc)");
+    return MTADGAT_OK;
+  }
+  launch_transpose(w_hh, wt, G, R, s);
   GruFwdParams P;
   P.gi = nullptr; P.S = S; P.hsrc = h_src; P.b_ih = b_ih; P.J = J; P.Hs = Hs; P.wt = wt; P.b_hh = b_hh;
   P.out = out; P.h_last = nullptr; P.gates = gates; P.B = B; P.n = n; P.H = R;
@@ -464,8 +497,13 @@ extern "C" int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const 
   GruBwdParams P;
   P.gates = gates; P.out = out; P.w_hh = w_hh; P.dout = dout; P.dh_last = nullptr; P.dgi = dgi; P.dghn = dghn;
   P.B = B; P.n = n; P.H = R;
-  int rc = launch_gru_bwd(P, s);
-  if (rc) return rc;
+  if (g_gru_impl == 1 && mtadgat_gru_tc_bwd_supported(R)) {
+    unsigned int* gmax = reinterpret_cast<unsigned int*>(dS + (size_t)n * J * G);
+    mtadgat_gru_tc_bwd_launch(gates, out, w_hh, dout, nullptr, gmax, dgi, dghn, B, n, R, s);
+  } else {
+    int rc = launch_gru_bwd(P, s);
+    if (rc) return rc;
+  }
   MG_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * (size_t)G * R, s));
   MG_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)G, s));
   MG_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)G, s));

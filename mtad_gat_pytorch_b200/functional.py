@@ -249,6 +249,16 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db, None, None, None, None
 
 
+def set_gru_impl(name):
+    """'tc' (default): persistent tcgen05/TMEM recurrence, fp16 operands, fp32 accumulate + fp32 state;
+    'fp32': SIMT fp32 recurrence."""
+    check(lib.mtadgat_set_gru_impl({"fp32": 0, "tc": 1}[name]))
+
+
+def get_gru_impl():
+    return {0: "fp32", 1: "tc"}[lib.mtadgat_get_gru_impl()]
+
+
 def launch_count():
     return int(lib.mtadgat_launch_count())
 
