@@ -85,15 +85,23 @@ int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const float* w_hh
 int mtadgat_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int I, int O, int act,
                        float p_drop, const unsigned long long* seed, unsigned int rng_stream, void* stream);
 int mtadgat_linear_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx /*nullable*/,
-                       int dx_accumulate, float* dw, float* db, int M, int I, int O, int act, float p_drop,
-                       const unsigned long long* seed, unsigned int rng_stream, void* stream);
+                       int dx_accumulate, float* dw, float* db, float* scratch /* M*O floats; nullable if act=0,p=0 */,
+                       int M, int I, int O, int act, float p_drop, const unsigned long long* seed,
+                       unsigned int rng_stream, void* stream);
 
 /* ---- recurrence implementation: 1 (default) = persistent tcgen05/TMEM kernel, fp16 operands with fp32
  *      accumulation and fp32 hidden state (hidden sizes 8..256); 0 = fp32 SIMT kernel.  mtadgat_tc_probe runs one
  *      128 x N x K product through the same shared-memory operand layout (diagnostic / unit test). ---- */
 int mtadgat_set_gru_impl(int impl);
 int mtadgat_get_gru_impl(void);
-int mtadgat_tc_probe(const float* A, const float* Bm, float* D, int Mtot, int row0, int K, int N, void* stream);
+/* GEMM-shaped stages (conv, projections, heads, weight gradients): 1 (default) = tcgen05 kind::tf32 with the 3xTF32
+ * split (fp32-level accuracy), 0 = SIMT fp32. */
+int mtadgat_set_gemm_impl(int impl);
+int mtadgat_get_gemm_impl(void);
+int mtadgat_tc_probe(const float* A, const float* Bm, float* D, int Mtot, int row0, int K, int N, int b_mn_major,
+                     int mma_m, void* stream);
+int mtadgat_tc_mma_bench(int ntiles, int kchunks, int M, int N, int iters, int row_stride, int nissuers, int mode,
+                         long long* out_cycles, void* stream);
 
 /* ---- RNG plumbing ---- */
 int mtadgat_dropout_mask(float* out, long long numel, float p, const unsigned long long* seed,

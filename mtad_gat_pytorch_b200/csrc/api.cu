@@ -6,6 +6,7 @@
 
 static thread_local char g_err[512] = "";
 unsigned long long g_mtadgat_launches = 0;
+int g_mtadgat_gemm_impl = 1;   // 1 = tcgen05 3xTF32 GEMMs (tc_gemm.cuh), 0 = SIMT fp32 (gemm.cuh)
 
 void mtadgat_set_error(const char* fmt, ...) {
   va_list ap;
@@ -18,6 +19,12 @@ extern "C" const char* mtadgat_last_error(void) { return g_err; }
 extern "C" int mtadgat_abi_version(void) { return MTADGAT_ABI_VERSION; }
 extern "C" unsigned long long mtadgat_launch_count(void) { return g_mtadgat_launches; }
 extern "C" void mtadgat_reset_launch_count(void) { g_mtadgat_launches = 0; }
+extern "C" int mtadgat_set_gemm_impl(int impl) {
+  MG_CHECK_ARG(impl == 0 || impl == 1, "set_gemm_impl: 0 (SIMT fp32) or 1 (tcgen05 3xTF32)");
+  g_mtadgat_gemm_impl = impl;
+  return MTADGAT_OK;
+}
+extern "C" int mtadgat_get_gemm_impl(void) { return g_mtadgat_gemm_impl; }
 
 namespace {
 __global__ void dropout_mask_kernel(float* out, long long numel, float p, float inv_keep,

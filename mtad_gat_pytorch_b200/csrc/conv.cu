@@ -81,6 +81,78 @@ struct DpreCols {
 
 }  // namespace
 
+// ---- tensor-core loader specialisations: index decoding hoisted out of the K loop ------------------------------
+namespace tcg {
+template <bool MASKED> struct OpA<ConvShiftLoad<MASKED>> {
+  using F = ConvShiftLoad<MASKED>;
+  struct Ctx { int b, t; };
+  static __device__ __forceinline__ Ctx line(const F& f, int, int m) { int b = m / f.n; return Ctx{b, m - b * f.n}; }
+  static __device__ __forceinline__ void load8(const F& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    int tau = k0 / f.k, ch = k0 - tau * f.k;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int ts = c.t + f.sgn * (tau - f.pad);
+      float val = 0.f;
+      if (k0 + j < kend && ts >= 0 && ts < f.n) {
+        long long o = ((long long)c.b * f.n + ts) * f.k + ch;
+        val = __ldg(f.src + o);
+        if (MASKED) val = (__ldg(f.y + o) > 0.f) ? val : 0.f;
+      }
+      v[j] = val;
+      if (++ch == f.k) { ch = 0; ++tau; }
+    }
+  }
+};
+template <> struct OpB<ConvWFwd> {      // B(kk=(tau,ci), n=co) = w[co, ci, tau]
+  struct Ctx { const float* p; };
+  static __device__ __forceinline__ Ctx line(const ConvWFwd& f, int, int co) { return Ctx{f.w + (long long)co * f.k * f.ks}; }
+  static __device__ __forceinline__ void load8(const ConvWFwd& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    int tau = k0 / f.k, ci = k0 - tau * f.k;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = (k0 + j < kend) ? __ldg(c.p + ci * f.ks + tau) : 0.f;
+      if (++ci == f.k) { ci = 0; ++tau; }
+    }
+  }
+};
+template <> struct OpB<ConvWBwd> {      // B(kk=(tau,co), n=ci) = w[co, ci, tau]
+  struct Ctx { const float* p; };
+  static __device__ __forceinline__ Ctx line(const ConvWBwd& f, int, int ci) { return Ctx{f.w + (long long)ci * f.ks}; }
+  static __device__ __forceinline__ void load8(const ConvWBwd& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    int tau = k0 / f.k, co = k0 - tau * f.k;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = (k0 + j < kend) ? __ldg(c.p + (long long)co * f.k * f.ks + tau) : 0.f;
+      if (++co == f.k) { co = 0; ++tau; }
+    }
+  }
+};
+template <> struct OpA<DpreT> {         // A(m=co, kk=(b,t)) = dy * (y>0)
+  struct Ctx { int co; };
+  static __device__ __forceinline__ Ctx line(const DpreT&, int, int co) { return Ctx{co}; }
+  static __device__ __forceinline__ void load8(const DpreT& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      long long o = (long long)(k0 + j) * f.k + c.co;
+      v[j] = (k0 + j < kend && __ldg(f.y + o) > 0.f) ? __ldg(f.dy + o) : 0.f;
+    }
+  }
+};
+template <> struct OpB<ConvXCols> {     // B(kk=(b,t), n=(tau,ci)) = xpad[b, t+tau-pad, ci]
+  struct Ctx { int shift, ci; };
+  static __device__ __forceinline__ Ctx line(const ConvXCols& f, int, int nn) { int tau = nn / f.k; return Ctx{tau - f.pad, nn - tau * f.k}; }
+  static __device__ __forceinline__ void load8(const ConvXCols& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    int b = k0 / f.n, t = k0 - b * f.n;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int ts = t + c.shift;
+      v[j] = (k0 + j < kend && ts >= 0 && ts < f.n) ? __ldg(f.x + ((long long)b * f.n + ts) * f.k + c.ci) : 0.f;
+      if (++t == f.n) { t = 0; ++b; }
+    }
+  }
+};
+}  // namespace tcg
+
 extern "C" int mtadgat_conv_relu_fwd(const float* x, const float* w, const float* bias, float* y, int B, int n,
                                      int k, int ks, void* stream) {
   MG_CHECK_ARG(x && w && bias && y, "conv_relu_fwd: null pointer");

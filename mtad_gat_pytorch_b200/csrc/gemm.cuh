@@ -6,6 +6,7 @@
 // layout and nothing is permuted, padded, concatenated or materialised in HBM first.
 #pragma once
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
 
@@ -18,6 +19,31 @@ struct Strided2 {
     return __ldg(p + (long long)z * sz + (long long)i * si + (long long)j * sj);
   }
 };
+
+namespace tcg {
+template <bool F>
+struct OpA<Strided2<F>> {
+  struct Ctx { const float* p; };
+  static __device__ __forceinline__ Ctx line(const Strided2<F>& f, int z, int m) {
+    return Ctx{f.p + (long long)z * f.sz + (long long)m * f.si};
+  }
+  static __device__ __forceinline__ void load8(const Strided2<F>& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < kend) ? __ldg(c.p + (long long)(k0 + j) * f.sj) : 0.f;
+  }
+};
+template <bool F>
+struct OpB<Strided2<F>> {
+  struct Ctx { const float* p; };
+  static __device__ __forceinline__ Ctx line(const Strided2<F>& f, int z, int n) {
+    return Ctx{f.p + (long long)z * f.sz + (long long)n * f.sj};
+  }
+  static __device__ __forceinline__ void load8(const Strided2<F>& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < kend) ? __ldg(c.p + (long long)(k0 + j) * f.si) : 0.f;
+  }
+};
+}  // namespace tcg
 
 // C store: v (+bias[n]) -> act -> write / accumulate / atomicAdd at p[z*sz + m*sm + n*sn]
 struct StStrided {
@@ -113,6 +139,8 @@ __global__ void __launch_bounds__(256) gemm_kernel(int M, int N, int K, int klen
 template <class AL, class BL, class CS>
 static inline void launch_gemm_batched(int batch, int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
+  // dispatch must not depend on the batch-derived dimension M: a window's result may not depend on its batch
+  if (g_mtadgat_gemm_impl == 1 && N >= 16 && K >= 16) { tcg::launch_batched(batch, M, N, K, A, Bm, C, s); return; }
   dim3 g(cdiv(N, GEMM_BN), cdiv(M, GEMM_BM), batch);
   gemm_kernel<AL, BL, CS><<<g, 256, 0, s>>>(M, N, K, K, 0, A, Bm, C);
   MG_COUNT_LAUNCH();
@@ -122,6 +150,7 @@ static inline void launch_gemm_batched(int batch, int M, int N, int K, AL A, BL 
 template <class AL, class BL, class CS>
 static inline void launch_gemm_splitk(int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s, int target_ctas = 592) {
   if (M <= 0 || N <= 0) return;
+  if (g_mtadgat_gemm_impl == 1 && M >= 32 && N >= 16) { tcg::launch_splitk(M, N, K, A, Bm, C, s, 296); return; }
   int tiles = cdiv(N, GEMM_BN) * cdiv(M, GEMM_BM);
   int splits = max(1, min(cdiv(K, 4 * GEMM_BK), cdiv(target_ctas, tiles)));
   int klen = cdiv(cdiv(K, splits), GEMM_BK) * GEMM_BK;

@@ -1,40 +1,52 @@
-// GRULayer / RNNDecoder recurrences (reference modules.py:220-257; torch.nn.GRU gate order r,z,n, h0 = 0).
+// GRULayer / RNNDecoder (reference modules.py:220-257; torch.nn.GRU gate order r,z,n, h0 = 0): C ABI entry
+// points, the GEMM glue around the recurrence, and the fp32 SIMT recurrence (impl 0).  The tcgen05 recurrence
+// (impl 1, default) lives in gru_tc.cu.
 //
-// Baseline path: the input projection of all n steps is one GEMM (reading the three (B,n,k) tensors that the
-// reference concatenates at mtad_gat.py:71 as three K-slices -- the concat never exists), then a persistent
-// recurrent kernel keeps a tile of BT windows' hidden state in shared memory for all n steps.
-// The decoder's input is the reference's scrambled repeat of h_end (modules.py:279):
+// The input projection of all n steps is one GEMM that reads the three (B,n,k) tensors the reference concatenates
+// at mtad_gat.py:71 as three K-slices -- the concat never exists.  The decoder's input is the reference's
+// scrambled repeat of h_end (modules.py:279):
 //   rep[b,t,c] = h_end[b,(t*H+c)//n]   =>   W_ih rep[b,t,:] = sum_j h_end[b,m0(t)+j] * S[t,j,:]
 // with S[t,j,g] = sum_{c:(t*H+c)//n = m0(t)+j} W_ih[g,c]  -- J = O(H/n + 2) FMAs per gate instead of H.
 #include "gemm.cuh"
+#include "gru_common.cuh"
 #include "../../include/mtadgat.h"
 
-// tensor-core recurrence (gru_tc.cu)
-int mtadgat_gru_tc_supported(int H);
-int mtadgat_gru_tc_fwd_launch(const float* gi, const float* S, const float* hsrc, const float* b_ih, int J, int Hs,
-                              const float* w_hh, const float* b_hh, float* out, float* h_last, float* gates, int B,
-                              int n, int H, cudaStream_t s);
-int mtadgat_gru_tc_bwd_supported(int H);
-int mtadgat_gru_tc_bwd_launch(const float* gates, const float* out, const float* w_hh, const float* dout,
-                              const float* dh_last, unsigned int* gmax_bits, float* dgi, float* dghn, int B, int n,
-                              int H, cudaStream_t s);
-static int g_gru_impl = 1;   // 0 = fp32 SIMT recurrence, 1 = tcgen05 fp16-operand recurrence (fp32 accumulate/state)
+// 0 = fp32 SIMT recurrence; 1 = tensor cores (cluster kernel where the hidden size allows, else the one-CTA tcgen05
+// kernel, else SIMT); 2 = tensor cores, one-CTA kernel only (kept for comparison)
+static int g_gru_impl = 1;
+static inline size_t al4(size_t x) { return (x + 3) & ~(size_t)3; }   // keep every segment 16-byte aligned   // 0 = fp32 SIMT recurrence, 1 = tcgen05 fp16-operand recurrence (fp32 accumulate/state)
 
 namespace {
 
-constexpr int BT = 8;   // windows per CTA in the recurrent kernels
+constexpr int BT = 8;   // windows per CTA in the SIMT recurrent kernels
 
-// ---- functors ----------------------------------------------------------------------------------
-// A(m=(b,t), kk) over three column slices
-struct Cat3A {
+// ---- functors over window-tiled row order r = (tile*n + t)*16 + w ----------------------------------------
+__device__ __forceinline__ float cat3_load(const float* x0, const float* x1, const float* x2, int k0, int k1, int k2,
+                                           long long row, int kk) {
+  if (kk < k0) return __ldg(x0 + row * k0 + kk);
+  kk -= k0;
+  if (kk < k1) return __ldg(x1 + row * k1 + kk);
+  kk -= k1;
+  return __ldg(x2 + row * k2 + kk);
+}
+// A(m=r, kk) = x_cat[(b,t), kk]
+struct Cat3AT {
   static constexpr bool fast_second = true;
-  const float *x0, *x1, *x2; int k0, k1, k2;
-  __device__ __forceinline__ float operator()(int, int m, int kk) const {
-    if (kk < k0) return __ldg(x0 + (long long)m * k0 + kk);
-    kk -= k0;
-    if (kk < k1) return __ldg(x1 + (long long)m * k1 + kk);
-    kk -= k1;
-    return __ldg(x2 + (long long)m * k2 + kk);
+  const float *x0, *x1, *x2; int k0, k1, k2, n, B;
+  __device__ __forceinline__ float operator()(int, int r, int kk) const {
+    int b, t; tiled_row_decode(r, n, b, t);
+    if (b >= B) return 0.f;
+    return cat3_load(x0, x1, x2, k0, k1, k2, (long long)b * n + t, kk);
+  }
+};
+// B(kk=r, n=col) = x_cat[(b,t), col]
+struct Cat3BT {
+  static constexpr bool fast_second = true;
+  const float *x0, *x1, *x2; int k0, k1, k2, n, B;
+  __device__ __forceinline__ float operator()(int, int r, int col) const {
+    int b, t; tiled_row_decode(r, n, b, t);
+    if (b >= B) return 0.f;
+    return cat3_load(x0, x1, x2, k0, k1, k2, (long long)b * n + t, col);
   }
 };
 // B(kk, n=g) = W[g, kk]  for a row-major (G, I) weight
@@ -43,60 +55,172 @@ struct WT {
   const float* w; int I;
   __device__ __forceinline__ float operator()(int, int kk, int g) const { return __ldg(w + (long long)g * I + kk); }
 };
-// store into three column slices (data gradient of the concatenated input)
-struct StCat3 {
-  float *d0, *d1, *d2; int k0, k1, k2; int acc0, acc1, acc2;
-  __device__ __forceinline__ void operator()(int, int m, int kk, float v, bool) const {
+// C(m=r, n=g) -> tiled[r][g] = v + bias[g]
+struct StTiledBias {
+  float* dst; const float* bias; int C;
+  __device__ __forceinline__ void operator()(int, int r, int g, float v, bool) const { dst[tiled_rc(r, g, C)] = v + __ldg(bias + g); }
+};
+// A(m=g, kk=r) = tiled[r][g]            (r-fast: 16 consecutive r are contiguous)
+struct TiledT {
+  static constexpr bool fast_second = true;
+  const float* src; int C;
+  __device__ __forceinline__ float operator()(int, int g, int r) const { return __ldg(src + tiled_rc(r, g, C)); }
+};
+// A(m=g, kk=r) = dgh[r][g] : first 2H channels from dgi_t, last H from dghn_t
+struct DghTT {
+  static constexpr bool fast_second = true;
+  const float* dgi; const float* dghn; int H;
+  __device__ __forceinline__ float operator()(int, int g, int r) const {
+    return g < 2 * H ? __ldg(dgi + tiled_rc(r, g, 3 * H)) : __ldg(dghn + tiled_rc(r, g - 2 * H, H));
+  }
+};
+// A(m=r, kk=g) = tiled[r][g]            (r-fast)
+struct TiledA {
+  static constexpr bool fast_second = false;
+  const float* src; int C;
+  __device__ __forceinline__ float operator()(int, int r, int g) const { return __ldg(src + tiled_rc(r, g, C)); }
+};
+// B(kk=r, n=u) = h_{t-1}[b,u] = out[b,t-1,u] (0 at t = 0)
+struct HprevBT {
+  static constexpr bool fast_second = true;
+  const float* out; int n, H, B;
+  __device__ __forceinline__ float operator()(int, int r, int u) const {
+    int b, t; tiled_row_decode(r, n, b, t);
+    if (t == 0 || b >= B) return 0.f;
+    return __ldg(out + ((long long)b * n + t - 1) * H + u);
+  }
+};
+// data gradient of the concatenated input: C(m=r, n=col) -> three column slices at row (b,t)
+struct StCat3T {
+  float *d0, *d1, *d2; int k0, k1, k2, n, B; int acc0, acc1, acc2;
+  __device__ __forceinline__ void operator()(int, int r, int kk, float v, bool) const {
+    int b, t; tiled_row_decode(r, n, b, t);
+    if (b >= B) return;
+    long long row = (long long)b * n + t;
     float* q; int acc;
-    if (kk < k0) { q = d0 ? d0 + (long long)m * k0 + kk : nullptr; acc = acc0; }
-    else if (kk < k0 + k1) { q = d1 ? d1 + (long long)m * k1 + (kk - k0) : nullptr; acc = acc1; }
-    else { q = d2 ? d2 + (long long)m * k2 + (kk - k0 - k1) : nullptr; acc = acc2; }
+    if (kk < k0) { q = d0 ? d0 + row * k0 + kk : nullptr; acc = acc0; }
+    else if (kk < k0 + k1) { q = d1 ? d1 + row * k1 + (kk - k0) : nullptr; acc = acc1; }
+    else { q = d2 ? d2 + row * k2 + (kk - k0 - k1) : nullptr; acc = acc2; }
     if (!q) return;
     *q = acc ? (*q + v) : v;
   }
 };
-// A(m=g, kk=(b,t)) = dgi[(b,t), g]           (for dW_ih)
-struct DgiT {
-  static constexpr bool fast_second = false;
-  const float* dgi; int G;
-  __device__ __forceinline__ float operator()(int, int g, int kk) const { return __ldg(dgi + (long long)kk * G + g); }
-};
-// A(m=g, kk=(b,t)) = dgh[(b,t), g] : first 2H columns from dgi, last H from dghn   (for dW_hh)
-struct DghT {
-  static constexpr bool fast_second = false;
-  const float* dgi; const float* dghn; int H;
-  __device__ __forceinline__ float operator()(int, int g, int kk) const {
-    return g < 2 * H ? __ldg(dgi + (long long)kk * 3 * H + g) : __ldg(dghn + (long long)kk * H + (g - 2 * H));
+
+
+}  // namespace
+
+// ---- tensor-core loader specialisations (tc_gemm.cuh operand protocol) for the GRU functors ------------------
+namespace tcg {
+template <> struct OpA<Cat3AT> {
+  struct Ctx { long long row; };
+  static __device__ __forceinline__ Ctx line(const Cat3AT& f, int, int r) {
+    int b, t; tiled_row_decode(r, f.n, b, t);
+    return Ctx{b < f.B ? (long long)b * f.n + t : -1};
+  }
+  static __device__ __forceinline__ void load8(const Cat3AT& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      v[j] = (c.row >= 0 && k0 + j < kend) ? cat3_load(f.x0, f.x1, f.x2, f.k0, f.k1, f.k2, c.row, k0 + j) : 0.f;
   }
 };
-struct DghCols {
-  static constexpr bool fast_second = true;
-  const float* dgi; const float* dghn; int H;
-  __device__ __forceinline__ float operator()(int, int m, int g) const {
-    return g < 2 * H ? __ldg(dgi + (long long)m * 3 * H + g) : __ldg(dghn + (long long)m * H + (g - 2 * H));
+template <> struct OpB<WT> {
+  struct Ctx { const float* p; };
+  static __device__ __forceinline__ Ctx line(const WT& f, int, int g) { return Ctx{f.w + (long long)g * f.I}; }
+  static __device__ __forceinline__ void load8(const WT&, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < kend) ? __ldg(c.p + k0 + j) : 0.f;
   }
 };
-// B(kk=(b,t), n) = x_cat[(b,t), n]
-struct Cat3B {
-  static constexpr bool fast_second = true;
-  const float *x0, *x1, *x2; int k0, k1, k2;
-  __device__ __forceinline__ float operator()(int, int m, int kk) const {
-    if (kk < k0) return __ldg(x0 + (long long)m * k0 + kk);
-    kk -= k0;
-    if (kk < k1) return __ldg(x1 + (long long)m * k1 + kk);
-    kk -= k1;
-    return __ldg(x2 + (long long)m * k2 + kk);
+// 8 consecutive tiled rows of one channel are 32 contiguous, 32-byte aligned bytes
+__device__ __forceinline__ void load_tiled8(const float* src, int C, int ch, int k0, int kend, float (&v)[8]) {
+  if (k0 + 8 <= kend) {
+    const float4* p = reinterpret_cast<const float4*>(src + ((size_t)(k0 >> 4) * C + ch) * 16 + (k0 & 15));
+    float4 a = __ldg(p), b = __ldg(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < kend) ? __ldg(src + tiled_rc(k0 + j, ch, C)) : 0.f;
+  }
+}
+template <> struct OpA<TiledT> {
+  struct Ctx { int g; };
+  static __device__ __forceinline__ Ctx line(const TiledT&, int, int g) { return Ctx{g}; }
+  static __device__ __forceinline__ void load8(const TiledT& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    load_tiled8(f.src, f.C, c.g, k0, kend, v);
   }
 };
-// B(kk=(b,t), n=u) = h_{t-1}[b,u] = out[b,t-1,u] (0 at t = 0)
-struct HprevB {
-  static constexpr bool fast_second = true;
-  const float* out; int n, H;
-  __device__ __forceinline__ float operator()(int, int kk, int u) const {
-    int t = kk % n;
-    return t == 0 ? 0.f : __ldg(out + (long long)(kk - 1) * H + u);
+template <> struct OpA<DghTT> {
+  struct Ctx { int g; };
+  static __device__ __forceinline__ Ctx line(const DghTT&, int, int g) { return Ctx{g}; }
+  static __device__ __forceinline__ void load8(const DghTT& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    if (c.g < 2 * f.H) load_tiled8(f.dgi, 3 * f.H, c.g, k0, kend, v);
+    else load_tiled8(f.dghn, f.H, c.g - 2 * f.H, k0, kend, v);
   }
 };
+template <> struct OpA<TiledA> {
+  struct Ctx { const float* p; };
+  static __device__ __forceinline__ Ctx line(const TiledA& f, int, int r) {
+    return Ctx{f.src + (size_t)(r >> 4) * f.C * 16 + (r & 15)};
+  }
+  static __device__ __forceinline__ void load8(const TiledA&, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (k0 + j < kend) ? __ldg(c.p + (size_t)(k0 + j) * 16) : 0.f;
+  }
+};
+// B(k = tiled row, n = column of the concatenated input): the 8 rows are 8 consecutive windows of one (tile, t)
+template <> struct OpB<Cat3BT> {
+  struct Ctx { const float* base; int stride; };
+  static __device__ __forceinline__ Ctx line(const Cat3BT& f, int, int col) {
+    if (col < f.k0) return Ctx{f.x0 + col, f.k0};
+    col -= f.k0;
+    if (col < f.k1) return Ctx{f.x1 + col, f.k1};
+    return Ctx{f.x2 + (col - f.k1), f.k2};
+  }
+  static __device__ __forceinline__ void load8(const Cat3BT& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    const int q = k0 >> 4, tile = q / f.n, t = q - tile * f.n, w0 = k0 & 15;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int b = tile * 16 + w0 + j;
+      v[j] = (k0 + j < kend && b < f.B) ? __ldg(c.base + ((long long)b * f.n + t) * c.stride) : 0.f;
+    }
+  }
+};
+template <> struct OpB<HprevBT> {
+  struct Ctx { int u; };
+  static __device__ __forceinline__ Ctx line(const HprevBT&, int, int u) { return Ctx{u}; }
+  static __device__ __forceinline__ void load8(const HprevBT& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    const int q = k0 >> 4, tile = q / f.n, t = q - tile * f.n, w0 = k0 & 15;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int b = tile * 16 + w0 + j;
+      v[j] = (t > 0 && k0 + j < kend && b < f.B) ? __ldg(f.out + ((long long)b * f.n + t - 1) * f.H + c.u) : 0.f;
+    }
+  }
+};
+}  // namespace tcg
+
+namespace {
+
+// out[c] += sum over rows R=(tile,t) and the 16 windows of tiled[R][c][w]
+__global__ void __launch_bounds__(256) colsum_tiled_kernel(const float* __restrict__ src, int R, int C, int rlen,
+                                                          float* __restrict__ out) {
+  const int c16 = blockIdx.x * 256 + threadIdx.x;
+  const int rbeg = blockIdx.y * rlen, rend = min(R, rbeg + rlen);
+  float s = 0.f;
+  if (c16 < C * 16)
+    for (int r = rbeg; r < rend; ++r) s += __ldg(src + (size_t)r * C * 16 + c16);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 15) == 0 && c16 < C * 16) atomicAdd(out + (c16 >> 4), s);
+}
+static void launch_colsum_tiled(const float* src, int R, int C, float* out, cudaStream_t s) {
+  int nb = cdiv((long long)C * 16, 256);
+  int rsplit = max(1, min(cdiv(R, 16), cdiv(592, nb)));
+  int rlen = cdiv(R, rsplit);
+  rsplit = cdiv(R, rlen);
+  colsum_tiled_kernel<<<dim3(nb, rsplit), 256, 0, s>>>(src, R, C, rlen, out);
+  MG_COUNT_LAUNCH();
+}
 
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
   // dst[c][r] = src[r][c]
@@ -141,46 +265,44 @@ __global__ void rep_dw_kernel(const float* __restrict__ dS, int n, int Hs, int G
   }
   dw_ih[idx] = acc;
 }
-// dS[t][j][g] = sum_b dgi[b,t,g] * hsrc[b, m0[t]+j]
-__global__ void rep_dS_kernel(const float* __restrict__ dgi, const float* __restrict__ hsrc, int B, int n, int Hs, int G,
-                              int J, float* __restrict__ dS) {
+// dS[t][j][g] = sum_b dgi[b,t,g] * hsrc[b, m0[t]+j]        (dgi window-tiled)
+__global__ void rep_dS_kernel(const float* __restrict__ dgi_t, const float* __restrict__ hsrc, int B, int n, int Hs,
+                              int G, int J, float* __restrict__ dS) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * J * G) return;
   int g = idx % G, j = (idx / G) % J, t = idx / (G * J);
   int m = (int)(((long long)t * Hs) / n) + j;
   float acc = 0.f;
   if (m < Hs)
-    for (int b = 0; b < B; ++b) acc += dgi[((long long)b * n + t) * G + g] * hsrc[(long long)b * Hs + m];
+    for (int b = 0; b < B; ++b) acc += dgi_t[tiled_idx(b, t, g, n, G)] * hsrc[(long long)b * Hs + m];
   dS[idx] = acc;
 }
 // dhsrc[b][m] (+)= sum_{t,j: m0[t]+j == m} sum_g dgi[b,t,g] S[t][j][g]      one warp per (b,m)
-__global__ void rep_dh_kernel(const float* __restrict__ dgi, const float* __restrict__ S, int B, int n, int Hs, int G,
+__global__ void rep_dh_kernel(const float* __restrict__ dgi_t, const float* __restrict__ S, int B, int n, int Hs, int G,
                               int J, float* __restrict__ dh, int accumulate) {
   int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (wid >= B * Hs) return;
   int m = wid % Hs, b = wid / Hs;
-  // t such that m0[t] <= m <= m0[t]+J-1, i.e. (t*Hs)//n in [m-J+1, m]
   float acc = 0.f;
   int tlo = (int)(((long long)max(m - J + 1, 0) * n) / Hs);
   int thi = (int)min((long long)n - 1, (((long long)(m + 1) * n) / Hs));
   for (int t = tlo; t <= thi; ++t) {
     int j = m - (int)(((long long)t * Hs) / n);
     if (j < 0 || j >= J) continue;
-    const float* dg = dgi + ((long long)b * n + t) * G;
     const float* s = S + ((long long)t * J + j) * G;
-    for (int g = lane; g < G; g += 32) acc = fmaf(dg[g], s[g], acc);
+    for (int g = lane; g < G; g += 32) acc = fmaf(dgi_t[tiled_idx(b, t, g, n, G)], s[g], acc);
   }
   acc = warp_sum(acc);
   if (lane == 0) dh[wid] = accumulate ? dh[wid] + acc : acc;
 }
 
-// ---- recurrent forward ------------------------------------------------------------------------------
+// ---- fp32 SIMT recurrent forward ------------------------------------------------------------------------
 struct GruFwdParams {
-  const float* gi;        // (B,n,3H) incl. b_ih, or nullptr in rep mode
+  const float* gi;        // window-tiled (Bp/16,n,3H,16) incl. b_ih, or nullptr in rep mode
   const float* S; const float* hsrc; const float* b_ih; int J, Hs;   // rep mode
   const float* wt;        // (H, 3H) = W_hh^T
   const float* b_hh;
-  float* out; float* h_last; float* gates;   // out (B,n,H) / gates (B,n,4H) may be null
+  float* out; float* h_last; float* gates;   // out (B,n,H) standard / gates tiled (Bp/16,n,4H,16); may be null
   int B, n, H;
 };
 
@@ -194,7 +316,6 @@ __global__ void __launch_bounds__(1024) gru_fwd_kernel(GruFwdParams P) {
   for (int i = tid; i < H * BT; i += nth) hs[i] = 0.f;
   __syncthreads();
   for (int t = 0; t < n; ++t) {
-    // phase 1: gh = W_hh h + b_hh
     for (int g = tid; g < G; g += nth) {
       float acc[BT];
       float bb = __ldg(P.b_hh + g);
@@ -215,15 +336,20 @@ __global__ void __launch_bounds__(1024) gru_fwd_kernel(GruFwdParams P) {
       for (int w = 0; w < BT; ++w) ghs[g * (BT + 1) + w] = acc[w];
     }
     __syncthreads();
-    // phase 2: gates + state update
     for (int idx = tid; idx < H * BT; idx += nth) {
       int u = idx % H, w = idx / H;
       int b = b0 + w;
-      if (b >= P.B) continue;
+      if (b >= P.B) {
+        if (P.gates) {            // padded windows: keep the saved tensors finite
+          float* gp = P.gates + tiled_idx(b, t, u, n, 4 * H);
+          gp[0] = 0.f; gp[(size_t)H * 16] = 0.f; gp[(size_t)2 * H * 16] = 0.f; gp[(size_t)3 * H * 16] = 0.f;
+        }
+        continue;
+      }
       float gr, gz, gn;
       if (P.gi) {
-        const float* gp = P.gi + ((size_t)b * n + t) * G;
-        gr = __ldg(gp + u); gz = __ldg(gp + H + u); gn = __ldg(gp + 2 * H + u);
+        const float* gp = P.gi + tiled_idx(b, t, u, n, G);
+        gr = __ldg(gp); gz = __ldg(gp + (size_t)H * 16); gn = __ldg(gp + (size_t)2 * H * 16);
       } else {
         gr = __ldg(P.b_ih + u); gz = __ldg(P.b_ih + H + u); gn = __ldg(P.b_ih + 2 * H + u);
         int m0 = (int)(((long long)t * P.Hs) / n);
@@ -242,11 +368,10 @@ __global__ void __launch_bounds__(1024) gru_fwd_kernel(GruFwdParams P) {
       float hp = hs[u * BT + w];
       float hnew = (1.f - z) * nn + z * hp;
       hs[u * BT + w] = hnew;
-      size_t o = (size_t)b * n + t;
-      if (P.out) P.out[o * H + u] = hnew;
+      if (P.out) P.out[((size_t)b * n + t) * H + u] = hnew;
       if (P.gates) {
-        float* gp = P.gates + o * 4 * H;
-        gp[u] = r; gp[H + u] = z; gp[2 * H + u] = nn; gp[3 * H + u] = hn;
+        float* gp = P.gates + tiled_idx(b, t, u, n, 4 * H);
+        gp[0] = r; gp[(size_t)H * 16] = z; gp[(size_t)2 * H * 16] = nn; gp[(size_t)3 * H * 16] = hn;
       }
       if (t == n - 1 && P.h_last) P.h_last[(size_t)b * H + u] = hnew;
     }
@@ -254,11 +379,11 @@ __global__ void __launch_bounds__(1024) gru_fwd_kernel(GruFwdParams P) {
   }
 }
 
-// ---- recurrent backward (BPTT) ------------------------------------------------------------------------
+// ---- fp32 SIMT BPTT ------------------------------------------------------------------------------------------
 struct GruBwdParams {
-  const float* gates; const float* out; const float* w_hh;   // w_hh (3H,H) native layout
-  const float* dout; const float* dh_last;                    // either may be null
-  float* dgi; float* dghn;                                    // (B,n,3H), (B,n,H)
+  const float* gates; const float* out; const float* w_hh;   // gates tiled; out (B,n,H); w_hh (3H,H)
+  const float* dout; const float* dh_last;                    // (B,n,H) / (B,H); either may be null
+  float* dgi; float* dghn;                                    // tiled (Bp/16,n,3H,16), (Bp/16,n,H,16)
   int B, n, H;
 };
 
@@ -277,31 +402,31 @@ __global__ void __launch_bounds__(1024) gru_bwd_kernel(GruBwdParams P) {
   for (int t = n - 1; t >= 0; --t) {
     for (int idx = tid; idx < H * BT; idx += nth) {
       int u = idx % H, w = idx / H, b = b0 + w;
-      float dpr = 0.f, dpz = 0.f, dghn_ = 0.f, dhz = 0.f;
+      float dpr = 0.f, dpz = 0.f, dpn = 0.f, dghn_ = 0.f, dhz = 0.f;
       if (b < P.B) {
         size_t o = (size_t)b * n + t;
         float dh = dhs[u * BT + w];
         if (P.dout) dh += __ldg(P.dout + o * H + u);
-        const float* gp = P.gates + o * 4 * H;
-        float r = __ldg(gp + u), z = __ldg(gp + H + u), nn = __ldg(gp + 2 * H + u), hn = __ldg(gp + 3 * H + u);
+        const float* gp = P.gates + tiled_idx(b, t, u, n, 4 * H);
+        float r = __ldg(gp), z = __ldg(gp + (size_t)H * 16), nn = __ldg(gp + (size_t)2 * H * 16),
+              hn = __ldg(gp + (size_t)3 * H * 16);
         float hp = t > 0 ? __ldg(P.out + (o - 1) * H + u) : 0.f;
         float dn = dh * (1.f - z);
         float dz = dh * (hp - nn);
-        float dpn = dn * (1.f - nn * nn);
+        dpn = dn * (1.f - nn * nn);
         dpz = dz * z * (1.f - z);
         float dr = dpn * hn;
         dpr = dr * r * (1.f - r);
         dghn_ = dpn * r;
         dhz = dh * z;
-        float* q = P.dgi + o * G;
-        q[u] = dpr; q[H + u] = dpz; q[2 * H + u] = dpn;
-        P.dghn[o * H + u] = dghn_;
       }
+      float* q = P.dgi + tiled_idx(b, t, u, n, G);       // padded windows get zeros
+      q[0] = dpr; q[(size_t)H * 16] = dpz; q[(size_t)2 * H * 16] = dpn;
+      P.dghn[tiled_idx(b, t, u, n, H)] = dghn_;
       dg[u * BT + w] = dpr; dg[(H + u) * BT + w] = dpz; dg[(2 * H + u) * BT + w] = dghn_;
       dhs[u * BT + w] = dhz;
     }
     __syncthreads();
-    // dh_prev[u] += sum_g dgh[g] W_hh[g][u]; thread = (part, u), part splits the g range in 3
     for (int it = tid; it < 3 * H; it += nth) {
       int part = it / H, u = it - part * H;
       float acc[BT];
@@ -342,7 +467,7 @@ static int launch_gru_fwd(GruFwdParams& P, cudaStream_t s) {
   size_t smem = sizeof(float) * ((size_t)P.H * BT + (size_t)G * (BT + 1));
   if (smem > 200 * 1024) { mtadgat_set_error("gru_fwd: hidden size %d too large", P.H); return MTADGAT_ERR_UNSUPPORTED; }
   cudaFuncSetAttribute(gru_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  gru_fwd_kernel<<<cdiv(P.B, BT), threads, smem, s>>>(P);
+  gru_fwd_kernel<<<tiled_B(P.B) / BT, threads, smem, s>>>(P);
   MG_COUNT_LAUNCH();
   return MTADGAT_OK;
 }
@@ -352,7 +477,7 @@ static int launch_gru_bwd(GruBwdParams& P, cudaStream_t s) {
   size_t smem = sizeof(float) * ((size_t)P.H * BT + (size_t)G * BT);
   if (smem > 200 * 1024) { mtadgat_set_error("gru_bwd: hidden size %d too large", P.H); return MTADGAT_ERR_UNSUPPORTED; }
   cudaFuncSetAttribute(gru_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  gru_bwd_kernel<<<cdiv(P.B, BT), threads, smem, s>>>(P);
+  gru_bwd_kernel<<<tiled_B(P.B) / BT, threads, smem, s>>>(P);
   MG_COUNT_LAUNCH();
   return MTADGAT_OK;
 }
@@ -361,21 +486,49 @@ static void launch_transpose(const float* src, float* dst, int R, int C, cudaStr
   MG_COUNT_LAUNCH();
 }
 
+// recurrence dispatch: forward
+static int run_recurrence_fwd(const float* gi_t, const float* S, const float* hsrc, const float* b_ih, int J, int Hs,
+                              const float* w_hh, const float* b_hh, float* wt_scratch, float* out, float* h_last,
+                              float* gates_t, int B, int n, int H, cudaStream_t s) {
+  if (g_gru_impl == 1 && mtadgat_gru_cl_supported(H, gi_t ? 0 : Hs))
+    return mtadgat_gru_cl_fwd_launch(gi_t, S, hsrc, b_ih, J, Hs, w_hh, b_hh, out, h_last, gates_t, B, n, H, s);
+  if (g_gru_impl >= 1 && mtadgat_gru_tc_supported(H))
+    return mtadgat_gru_tc_fwd_launch(gi_t, S, hsrc, b_ih, J, Hs, w_hh, b_hh, out, h_last, gates_t, B, n, H, s);
+  launch_transpose(w_hh, wt_scratch, 3 * H, H, s);
+  GruFwdParams P;
+  P.gi = gi_t; P.S = S; P.hsrc = hsrc; P.b_ih = b_ih; P.J = J; P.Hs = Hs; P.wt = wt_scratch; P.b_hh = b_hh;
+  P.out = out; P.h_last = h_last; P.gates = gates_t; P.B = B; P.n = n; P.H = H;
+  return launch_gru_fwd(P, s);
+}
+// recurrence dispatch: BPTT (gmax = one spare device word)
+static int run_recurrence_bwd(const float* gates_t, const float* out, const float* w_hh, const float* dout,
+                              const float* dh_last, unsigned int* gmax, float* dgi_t, float* dghn_t, int B, int n, int H,
+                              cudaStream_t s) {
+  if (g_gru_impl == 1 && mtadgat_gru_cl_supported(H, 0))
+    return mtadgat_gru_cl_bwd_launch(gates_t, out, w_hh, dout, dh_last, gmax, dgi_t, dghn_t, B, n, H, s);
+  if (g_gru_impl >= 1 && mtadgat_gru_tc_supported(H))
+    return mtadgat_gru_tc_bwd_launch(gates_t, out, w_hh, dout, dh_last, gmax, dgi_t, dghn_t, B, n, H, s);
+  GruBwdParams P;
+  P.gates = gates_t; P.out = out; P.w_hh = w_hh; P.dout = dout; P.dh_last = dh_last; P.dgi = dgi_t; P.dghn = dghn_t;
+  P.B = B; P.n = n; P.H = H;
+  return launch_gru_bwd(P, s);
+}
+
 }  // namespace
 
 extern "C" int mtadgat_set_gru_impl(int impl) {
-  MG_CHECK_ARG(impl == 0 || impl == 1, "set_gru_impl: 0 (fp32 SIMT) or 1 (tcgen05)");
+  MG_CHECK_ARG(impl >= 0 && impl <= 2, "set_gru_impl: 0 (fp32 SIMT), 1 (tcgen05, cluster kernel preferred) or 2 (tcgen05 one-CTA kernel)");
   g_gru_impl = impl;
   return MTADGAT_OK;
 }
 extern "C" int mtadgat_get_gru_impl(void) { return g_gru_impl; }
 
-// saved (floats): wt (H*3H) | gates (B*n*4H, only if save) ; gi scratch is separate
+// saved (floats): wt (3H*H, padded to 4) | gates_t (Bp*n*4H, only if save)
 extern "C" long long mtadgat_gru_saved_floats(int B, int n, int H, int save) {
-  return (long long)((size_t)3 * H * H + (save ? (size_t)B * n * 4 * H : 0));
+  return (long long)(al4((size_t)3 * H * H) + (save ? (size_t)tiled_B(B) * n * 4 * H : 0));
 }
-extern "C" long long mtadgat_gru_fwd_scratch_floats(int B, int n, int H) { return (long long)((size_t)B * n * 3 * H); }
-extern "C" long long mtadgat_gru_bwd_scratch_floats(int B, int n, int H) { return (long long)((size_t)B * n * 4 * H + 4); }
+extern "C" long long mtadgat_gru_fwd_scratch_floats(int B, int n, int H) { return (long long)((size_t)tiled_B(B) * n * 3 * H); }
+extern "C" long long mtadgat_gru_bwd_scratch_floats(int B, int n, int H) { return (long long)((size_t)tiled_B(B) * n * 4 * H + 4); }
 
 extern "C" int mtadgat_gru_fwd(const float* x0, const float* x1, const float* x2, int k0, int k1, int k2,
                                const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
@@ -386,21 +539,11 @@ extern "C" int mtadgat_gru_fwd(const float* x0, const float* x1, const float* x2
   MG_CHECK_ARG((k1 == 0 || x1) && (k2 == 0 || x2), "gru_fwd: missing input slice");
   MG_CHECK_ARG(!save || out, "gru_fwd: training mode needs the per-step outputs");
   cudaStream_t s = (cudaStream_t)stream;
-  const int I = k0 + k1 + k2, G = 3 * H;
-  float* wt = saved; float* gates = save ? saved + (size_t)3 * H * H : nullptr;
+  const int I = k0 + k1 + k2, G = 3 * H, Bp = tiled_B(B);
+  float* wt = saved; float* gates = save ? saved + al4((size_t)3 * H * H) : nullptr;
   float* gi = scratch;
-  launch_gemm_batched(1, B * n, G, I, Cat3A{x0, x1, x2, k0, k1, k2}, WT{w_ih, I},
-                      StStrided{gi, 0, G, 1, b_ih, ACT_NONE, 0}, s);
-  if (g_gru_impl == 1 && mtadgat_gru_tc_supported(H)) {
-    mtadgat_gru_tc_fwd_launch(gi, nullptr, nullptr, nullptr, 0, 0, w_hh, b_hh, out, h_last, gates, B, n, H, s);
-    MG_CHECK_LAUNCH("gru_fwd(tc)");
-    return MTADGAT_OK;
-  }
-  launch_transpose(w_hh, wt, G, H, s);
-  GruFwdParams P;
-  P.gi = gi; P.S = nullptr; P.hsrc = nullptr; P.b_ih = nullptr; P.J = 0; P.Hs = 0; P.wt = wt; P.b_hh = b_hh;
-  P.out = out; P.h_last = h_last; P.gates = gates; P.B = B; P.n = n; P.H = H;
-  int rc = launch_gru_fwd(P, s);
+  launch_gemm_batched(1, Bp * n, G, I, Cat3AT{x0, x1, x2, k0, k1, k2, n, B}, WT{w_ih, I}, StTiledBias{gi, b_ih, G}, s);
+  int rc = run_recurrence_fwd(gi, nullptr, nullptr, nullptr, 0, 0, w_hh, b_hh, wt, out, h_last, gates, B, n, H, s);
   if (rc) return rc;
   MG_CHECK_LAUNCH("gru_fwd");
   return MTADGAT_OK;
@@ -414,31 +557,25 @@ extern "C" int mtadgat_gru_bwd(const float* x0, const float* x1, const float* x2
   MG_CHECK_ARG(x0 && w_ih && w_hh && out && saved && scratch && dw_ih && dw_hh && db_ih && db_hh, "gru_bwd: null pointer");
   MG_CHECK_ARG(dout || dh_last, "gru_bwd: need dout and/or dh_last");
   cudaStream_t s = (cudaStream_t)stream;
-  const int I = k0 + k1 + k2, G = 3 * H;
-  const float* gates = saved + (size_t)3 * H * H;
-  float* dgi = scratch; float* dghn = scratch + (size_t)B * n * G;
-  GruBwdParams P;
-  P.gates = gates; P.out = out; P.w_hh = w_hh; P.dout = dout; P.dh_last = dh_last; P.dgi = dgi; P.dghn = dghn;
-  P.B = B; P.n = n; P.H = H;
-  if (g_gru_impl == 1 && mtadgat_gru_tc_bwd_supported(H)) {
-    unsigned int* gmax = reinterpret_cast<unsigned int*>(scratch + (size_t)B * n * 4 * H);
-    mtadgat_gru_tc_bwd_launch(gates, out, w_hh, dout, dh_last, gmax, dgi, dghn, B, n, H, s);
-  } else {
-    int rc = launch_gru_bwd(P, s);
-    if (rc) return rc;
-  }
+  const int I = k0 + k1 + k2, G = 3 * H, Bp = tiled_B(B), Rt = Bp * n;
+  const float* gates = saved + al4((size_t)3 * H * H);
+  float* dgi = scratch; float* dghn = scratch + (size_t)Rt * G;
+  unsigned int* gmax = reinterpret_cast<unsigned int*>(scratch + (size_t)Rt * 4 * H);
+  int rc = run_recurrence_bwd(gates, out, w_hh, dout, dh_last, gmax, dgi, dghn, B, n, H, s);
+  if (rc) return rc;
   MG_CUDA(cudaMemsetAsync(dw_ih, 0, sizeof(float) * (size_t)G * I, s));
   MG_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * (size_t)G * H, s));
   MG_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)G, s));
   MG_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)G, s));
-  launch_gemm_splitk(G, I, B * n, DgiT{dgi, G}, Cat3B{x0, x1, x2, k0, k1, k2}, StAtomic2{dw_ih, I}, s);
-  launch_gemm_splitk(G, H, B * n, DghT{dgi, dghn, H}, HprevB{out, n, H}, StAtomic2{dw_hh, H}, s);
-  launch_colsum(B * n, G, Strided2<true>{dgi, 0, G, 1}, db_ih, s);
-  launch_colsum(B * n, G, DghCols{dgi, dghn, H}, db_hh, s);
+  launch_gemm_splitk(G, I, Rt, TiledT{dgi, G}, Cat3BT{x0, x1, x2, k0, k1, k2, n, B}, StAtomic2{dw_ih, I}, s);
+  launch_gemm_splitk(G, H, Rt, DghTT{dgi, dghn, H}, HprevBT{out, n, H, B}, StAtomic2{dw_hh, H}, s);
+  launch_colsum_tiled(dgi, Rt / 16, G, db_ih, s);
+  launch_colsum_tiled(dghn, Rt / 16, H, db_hh + 2 * H, s);
+  MG_CUDA(cudaMemcpyAsync(db_hh, db_ih, sizeof(float) * (size_t)2 * H, cudaMemcpyDeviceToDevice, s));
   if (dx0 || dx1 || dx2) {
-    // dx = dgi W_ih : A(m,kk=g) = dgi[m,g] ; B(kk=g, n=i) = w_ih[g, i]
-    launch_gemm_batched(1, B * n, I, G, Strided2<true>{dgi, 0, G, 1}, Strided2<true>{w_ih, 0, I, 1},
-                        StCat3{dx0, dx1, dx2, k0, k1, k2, acc0, acc1, acc2}, s);
+    // dx = dgi W_ih : A(m=r,kk=g) = dgi_t[r][g] ; B(kk=g, n=i) = w_ih[g, i]
+    launch_gemm_batched(1, Rt, I, G, TiledA{dgi, G}, Strided2<true>{w_ih, 0, I, 1},
+                        StCat3T{dx0, dx1, dx2, k0, k1, k2, n, B, acc0, acc1, acc2}, s);
   }
   MG_CHECK_LAUNCH("gru_bwd");
   return MTADGAT_OK;
@@ -446,15 +583,15 @@ extern "C" int mtadgat_gru_bwd(const float* x0, const float* x1, const float* x2
 
 // ---- decoder GRU on the scrambled repeat of h_src (modules.py:279) -------------------------------------
 extern "C" int mtadgat_rep_J(int n, int Hs) { return rep_J(n, Hs); }
-// saved (floats): wt (R*3R) | S (n*J*3R) | gates (B*n*4R if save)
+// saved (floats, each segment padded to 4): wt (3R*R) | S (n*J*3R) | gates_t (Bp*n*4R if save)
 extern "C" long long mtadgat_gru_rep_saved_floats(int B, int n, int Hs, int R, int save) {
   int J = rep_J(n, Hs);
-  return (long long)((size_t)3 * R * R + (size_t)n * J * 3 * R + (save ? (size_t)B * n * 4 * R : 0));
+  return (long long)(al4((size_t)3 * R * R) + al4((size_t)n * J * 3 * R) + (save ? (size_t)tiled_B(B) * n * 4 * R : 0));
 }
-// scratch for bwd: dgi (B*n*3R) | dghn (B*n*R) | dS (n*J*3R)
+// scratch for bwd: dgi_t (Bp*n*3R) | dghn_t (Bp*n*R) | dS (n*J*3R) | gmax
 extern "C" long long mtadgat_gru_rep_bwd_scratch_floats(int B, int n, int Hs, int R) {
   int J = rep_J(n, Hs);
-  return (long long)((size_t)B * n * 4 * R + (size_t)n * J * 3 * R + 4);
+  return (long long)((size_t)tiled_B(B) * n * 4 * R + (size_t)n * J * 3 * R + 4);
 }
 
 extern "C" int mtadgat_gru_rep_fwd(const float* h_src, const float* w_ih, const float* w_hh, const float* b_ih,
@@ -464,20 +601,11 @@ extern "C" int mtadgat_gru_rep_fwd(const float* h_src, const float* w_ih, const 
   MG_CHECK_ARG(B > 0 && n > 0 && Hs > 0 && R > 0, "gru_rep_fwd: bad shape");
   cudaStream_t s = (cudaStream_t)stream;
   const int G = 3 * R, J = rep_J(n, Hs);
-  float* wt = saved; float* S = saved + (size_t)3 * R * R;
-  float* gates = save ? S + (size_t)n * J * G : nullptr;
+  float* wt = saved; float* S = saved + al4((size_t)3 * R * R);
+  float* gates = save ? S + al4((size_t)n * J * G) : nullptr;
   rep_build_S_kernel<<<cdiv((long long)n * J * G, 256), 256, 0, s>>>(w_ih, n, Hs, G, J, S);
   MG_COUNT_LAUNCH();
-  if (g_gru_impl == 1 && mtadgat_gru_tc_supported(R)) {
-    mtadgat_gru_tc_fwd_launch(nullptr, S, h_src, b_ih, J, Hs, w_hh, b_hh, out, nullptr, gates, B, n, R, s);
-    MG_CHECK_LAUNCH("gru_rep_fwd(tc)");
-    return MTADGAT_OK;
-  }
-  launch_transpose(w_hh, wt, G, R, s);
-  GruFwdParams P;
-  P.gi = nullptr; P.S = S; P.hsrc = h_src; P.b_ih = b_ih; P.J = J; P.Hs = Hs; P.wt = wt; P.b_hh = b_hh;
-  P.out = out; P.h_last = nullptr; P.gates = gates; P.B = B; P.n = n; P.H = R;
-  int rc = launch_gru_fwd(P, s);
+  int rc = run_recurrence_fwd(nullptr, S, h_src, b_ih, J, Hs, w_hh, b_hh, wt, out, nullptr, gates, B, n, R, s);
   if (rc) return rc;
   MG_CHECK_LAUNCH("gru_rep_fwd");
   return MTADGAT_OK;
@@ -490,26 +618,20 @@ extern "C" int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const 
   MG_CHECK_ARG(h_src && w_ih && w_hh && out && saved && dout && scratch && dh_src && dw_ih && dw_hh && db_ih && db_hh,
                "gru_rep_bwd: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
-  const int G = 3 * R, J = rep_J(n, Hs);
-  const float* S = saved + (size_t)3 * R * R;
-  const float* gates = S + (size_t)n * J * G;
-  float* dgi = scratch; float* dghn = dgi + (size_t)B * n * G; float* dS = dghn + (size_t)B * n * R;
-  GruBwdParams P;
-  P.gates = gates; P.out = out; P.w_hh = w_hh; P.dout = dout; P.dh_last = nullptr; P.dgi = dgi; P.dghn = dghn;
-  P.B = B; P.n = n; P.H = R;
-  if (g_gru_impl == 1 && mtadgat_gru_tc_bwd_supported(R)) {
-    unsigned int* gmax = reinterpret_cast<unsigned int*>(dS + (size_t)n * J * G);
-    mtadgat_gru_tc_bwd_launch(gates, out, w_hh, dout, nullptr, gmax, dgi, dghn, B, n, R, s);
-  } else {
-    int rc = launch_gru_bwd(P, s);
-    if (rc) return rc;
-  }
+  const int G = 3 * R, J = rep_J(n, Hs), Bp = tiled_B(B), Rt = Bp * n;
+  const float* S = saved + al4((size_t)3 * R * R);
+  const float* gates = S + al4((size_t)n * J * G);
+  float* dgi = scratch; float* dghn = dgi + (size_t)Rt * G; float* dS = dghn + (size_t)Rt * R;
+  unsigned int* gmax = reinterpret_cast<unsigned int*>(dS + (size_t)n * J * G);
+  int rc = run_recurrence_bwd(gates, out, w_hh, dout, nullptr, gmax, dgi, dghn, B, n, R, s);
+  if (rc) return rc;
   MG_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * (size_t)G * R, s));
   MG_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)G, s));
   MG_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)G, s));
-  launch_gemm_splitk(G, R, B * n, DghT{dgi, dghn, R}, HprevB{out, n, R}, StAtomic2{dw_hh, R}, s);
-  launch_colsum(B * n, G, Strided2<true>{dgi, 0, G, 1}, db_ih, s);
-  launch_colsum(B * n, G, DghCols{dgi, dghn, R}, db_hh, s);
+  launch_gemm_splitk(G, R, Rt, DghTT{dgi, dghn, R}, HprevBT{out, n, R, B}, StAtomic2{dw_hh, R}, s);
+  launch_colsum_tiled(dgi, Rt / 16, G, db_ih, s);
+  launch_colsum_tiled(dghn, Rt / 16, R, db_hh + 2 * R, s);
+  MG_CUDA(cudaMemcpyAsync(db_hh, db_ih, sizeof(float) * (size_t)2 * R, cudaMemcpyDeviceToDevice, s));
   rep_dS_kernel<<<cdiv((long long)n * J * G, 256), 256, 0, s>>>(dgi, h_src, B, n, Hs, G, J, dS);
   MG_COUNT_LAUNCH();
   rep_dw_kernel<<<cdiv((long long)G * Hs, 256), 256, 0, s>>>(dS, n, Hs, G, J, dw_ih);

@@ -1,0 +1,528 @@
+// Cluster-parallel persistent GRU recurrence for sm_100a: one thread-block CLUSTER per tile of 16 windows.
+//
+// At batch 256 there are only 16 window tiles, and one SM per tile leaves the recurrence bound by that SM's
+// shared-memory operand bandwidth (the tcgen05 SS-MMA streams the resident W_hh: ~44 cycles per 128x16x16 MMA,
+// measured) and by its gate math.  Here the hidden units are split over the CS CTAs of a cluster (CS = 4 at
+// H = 150): CTA `rank` owns units [rank*Uc, rank*Uc+Uc) and keeps ONLY their W_hh rows resident -- the three gates
+// of its units packed into ONE 128-row A tile (rows [g*Uc, g*Uc+Uc) = gate g) -- so a step is 10 MMAs per SM
+// instead of 60, and the gate math of a step is spread over CS SMs.  Every CTA needs the full h_{t-1} as its B
+// operand: the epilogue threads write their fp16 h_t slice straight into the B-operand buffers of ALL CTAs of
+// the cluster (distributed shared memory, st.shared::cluster) and signal each CTA's mbarrier with a remote
+// release-arrive; the issuing thread acquires at cluster scope before the next step's MMAs.
+// Accumulator rows of one unit's three gates sit in three TMEM lanes, so four warps drain TMEM to a small
+// shared-memory stage and 160 threads (unit x 4 windows) do the gate math from there.
+// BPTT: same structure with A = W_hh^T rows of the CTA's units (M = 64 tile), K = all 3H gate rows, the B operand
+// (dgh_t, power-of-two scaled fp16) assembled from all CTAs' slices.
+#include <cuda_runtime.h>
+#include "tc.cuh"
+#include "gru_common.cuh"
+#include "../../include/mtadgat.h"
+
+namespace {
+
+constexpr int NB = 16;
+constexpr int EPI_THREADS = 256;
+constexpr int CL_THREADS = EPI_THREADS + 32;      // + one MMA-issuing warp (warp 8)
+constexpr int LBO_B = 256, SBO_B = 128;           // MN-major B operand: [k/8][w/8][k%8][w%8] fp16
+constexpr int SG_LD = 20;                         // staging row stride (floats): 16 windows + pad
+
+// ---- cluster / DSMEM primitives ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(tc::smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; it < (1u << 26); ++it)
+    if (mbar_try_wait_cluster(bar, parity)) return;
+  __trap();
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float sat_h(float v) { return fminf(fmaxf(v, -60000.f), 60000.f); }
+
+struct ClGeom { int CS, Uc; };
+// smallest cluster size whose per-CTA gate block (3*Uc rows) fits one 128-row tile and whose unit block fits M = 64
+static bool cl_geom(int H, ClGeom& g) {
+  if (H < 8) return false;
+  for (int cs = 2; cs <= 8; cs *= 2) {
+    int uc = (((H + cs - 1) / cs) + 7) & ~7;
+    if (3 * uc <= 128 && uc <= 64) { g.CS = cs; g.Uc = uc; return true; }
+  }
+  return false;
+}
+
+// ==========================================================================================================
+// forward
+// ==========================================================================================================
+struct ClFwdParams {
+  const float* gi;                                    // tiled (Bp/16,n,3H,16) incl. b_ih, or nullptr in rep mode
+  const float* S; const float* hsrc; const float* b_ih; int J, Hs;
+  const float* w_hh; const float* b_hh;
+  float* out; float* h_last; float* gates;            // out (B,n,H) | h_last (B,H) | gates tiled (Bp/16,n,4H,16)
+  int B, n, H, CS, Uc;
+};
+
+static size_t cl_fwd_smem(int H, int Hs_rep) {
+  int Kp = (H + 15) & ~15, KC = Kp / 8;
+  return (size_t)KC * 128 * 16 + 2 * (size_t)KC * LBO_B + (size_t)128 * SG_LD * 4 + (size_t)NB * Hs_rep * 4 + 128;
+}
+
+__global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int H = P.H, G = 3 * H, n = P.n, CS = P.CS, Uc = P.Uc;
+  const int Kp = (H + 15) & ~15, KC = Kp / 8;
+  const int lboA = 128 * 16;
+  uint8_t* sA = smem_raw;                                   // [KC][128 rows][16 B]
+  uint8_t* sB = sA + (size_t)KC * lboA;                     // [2][KC][256 B]
+  float* sG = reinterpret_cast<float*>(sB + 2 * (size_t)KC * LBO_B);     // [128][SG_LD]
+  float* sHs = sG + 128 * SG_LD;                            // rep mode: h_src tile [16][Hs]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sHs) +
+                                               (P.gi ? 0 : (((size_t)NB * P.Hs * 4 + 15) & ~(size_t)15)));
+  uint64_t* acc_bar = bars;        // local: MMA commit -> epilogue
+  uint64_t* h_bar = bars + 1;      // cluster-wide: all CTAs' epilogue warps -> this CTA's MMA issuer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  const int tile = blockIdx.x / CS, b0 = tile * NB;
+  const int u0 = rank * Uc, nu = max(0, min(Uc, H - u0));
+
+  // ---- one-time staging: this CTA's W_hh rows (3 gates x Uc units) -> fp16 canonical layout; h_0 = 0 ----
+  for (int idx = tid; idx < 128 * Kp; idx += CL_THREADS) {
+    int row = idx / Kp, k = idx - row * Kp;
+    int g = row / Uc, i = row - g * Uc;
+    float v = (g < 3 && i < nu && k < H) ? __ldg(P.w_hh + ((size_t)g * H + u0 + i) * H + k) : 0.f;
+    *reinterpret_cast<__half*>(sA + (size_t)(k >> 3) * lboA + (size_t)row * 16 + (k & 7) * 2) = __float2half_rn(v);
+  }
+  for (int idx = tid; idx < (2 * KC * LBO_B) / 4; idx += CL_THREADS) reinterpret_cast<uint32_t*>(sB)[idx] = 0u;
+  if (!P.gi)
+    for (int idx = tid; idx < NB * P.Hs; idx += CL_THREADS) {
+      int w = idx / P.Hs, m = idx - w * P.Hs;
+      sHs[idx] = (b0 + w < P.B) ? __ldg(P.hsrc + (size_t)(b0 + w) * P.Hs + m) : 0.f;
+    }
+  if (tid == 0) {
+    tc::mbar_init(acc_bar, 1);
+    tc::mbar_init(h_bar, CS * (EPI_THREADS / 32));
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, 32);
+  fence_proxy_async_all();
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // every CTA's barriers and B buffers are initialised before any remote access
+  tc::tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == 8) {
+    // ================= MMA issuer (whole warp runs the loop; one elected lane issues) =================
+    const uint32_t idesc = tc::make_idesc_f16(128, NB, 0, /*b_mn_major=*/1);
+    const uint64_t ad0 = tc::make_smem_desc(tc::smem_u32(sA), lboA, 128);
+    const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
+    const uint32_t ainc = (uint32_t)(2 * lboA) >> 4, binc = (uint32_t)(2 * LBO_B) >> 4;
+    const int nkc = Kp / 16;
+    for (int t = 0; t < n; ++t) {
+      if (t > 0) mbar_wait_cluster(h_bar, (t - 1) & 1);
+      fence_proxy_async_all();
+      tc::tc_fence_after();
+      const uint64_t bd0 = tc::make_smem_desc(tc::smem_u32(sB) + (uint32_t)((t & 1) * KC * LBO_B), LBO_B, SBO_B);
+      uint32_t alo = alo0, blo = (uint32_t)bd0;
+      const uint32_t bhi = (uint32_t)(bd0 >> 32);
+      for (int kc = 0; kc < nkc; ++kc) {
+        if (tc::elect_one()) tc::mma_f16_ss_lohi(tbase, alo, ahi, blo, bhi, idesc, kc > 0 ? 1u : 0u);
+        alo += ainc; blo += binc;
+      }
+      if (tc::elect_one()) tc::mma_commit(acc_bar);
+      __syncwarp();
+    }
+  } else {
+    // ================= epilogue: thread = (local unit i, 4 windows) =================
+    const int i = tid >> 2, wq = tid & 3, wb = 4 * wq;
+    const bool valid = i < nu;
+    const int u = u0 + i;
+    float bhr = 0.f, bhz = 0.f, bhn = 0.f, bir = 0.f, biz = 0.f, bin = 0.f;
+    if (valid) {
+      bhr = __ldg(P.b_hh + u); bhz = __ldg(P.b_hh + H + u); bhn = __ldg(P.b_hh + 2 * H + u);
+      if (!P.gi) { bir = __ldg(P.b_ih + u); biz = __ldg(P.b_ih + H + u); bin = __ldg(P.b_ih + 2 * H + u); }
+    }
+    float h[4] = {0.f, 0.f, 0.f, 0.f};
+    // byte offset of (unit u, windows wb..wb+3) inside one B buffer
+    const uint32_t hoff = (uint32_t)(u >> 3) * LBO_B + (uint32_t)(wq >> 1) * SBO_B + (uint32_t)(u & 7) * 16 + (uint32_t)(wq & 1) * 8;
+    const uint32_t sB_addr = tc::smem_u32(sB), hbar_addr = tc::smem_u32(h_bar);
+    const size_t gi_step = (size_t)G * 16, gt_step = (size_t)4 * H * 16;
+    const float* gi_p = (P.gi && valid) ? P.gi + ((size_t)tile * n * G + u) * 16 + wb : nullptr;
+    float* gt_p = (P.gates && valid) ? P.gates + ((size_t)tile * n * 4 * H + u) * 16 + wb : nullptr;
+    float* out_p = (P.out && valid) ? P.out + ((size_t)(b0 + wb) * n) * H + u : nullptr;
+    const int nvalid_w = max(0, min(4, P.B - (b0 + wb)));
+    const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+
+    for (int t = 0; t < n; ++t) {
+      // input-side pre-activations (independent of the recurrence; issued before the wait)
+      float gr[4], gz[4], gn[4];
+      if (P.gi) {
+        if (valid) {
+          const float4* p = reinterpret_cast<const float4*>(gi_p + (size_t)t * gi_step);
+          float4 a = __ldg(p), c = __ldg(p + (size_t)H * 4), e = __ldg(p + (size_t)2 * H * 4);
+          gr[0] = a.x; gr[1] = a.y; gr[2] = a.z; gr[3] = a.w;
+          gz[0] = c.x; gz[1] = c.y; gz[2] = c.z; gz[3] = c.w;
+          gn[0] = e.x; gn[1] = e.y; gn[2] = e.z; gn[3] = e.w;
+        } else {
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { gr[w] = 0.f; gz[w] = 0.f; gn[w] = 0.f; }
+        }
+      } else {
+        const int m0 = (int)(((long long)t * P.Hs) / n);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { gr[w] = bir; gz[w] = biz; gn[w] = bin; }
+        if (valid)
+          for (int j = 0; j < P.J; ++j) {
+            int m = m0 + j;
+            if (m >= P.Hs) break;
+            const float* sp = P.S + ((size_t)t * P.J + j) * G + u;
+            float sr = __ldg(sp), sz = __ldg(sp + H), sn = __ldg(sp + 2 * H);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              float hv = sHs[(wb + w) * P.Hs + m];
+              gr[w] = fmaf(hv, sr, gr[w]); gz[w] = fmaf(hv, sz, gz[w]); gn[w] = fmaf(hv, sn, gn[w]);
+            }
+          }
+      }
+      // drain TMEM -> staging (warps 0..3 own the 128 lanes)
+      if (warp < 4) {
+        tc::mbar_wait(acc_bar, t & 1);
+        tc::tc_fence_after();
+        float v[16];
+        tc::tmem_ld16(tlane, v);
+        tc::tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(sG + (size_t)(warp * 32 + lane) * SG_LD);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);   dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        dst[2] = make_float4(v[8], v[9], v[10], v[11]); dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+        tc::tc_fence_before();
+      }
+      named_bar_sync(1, EPI_THREADS);
+      if (valid) {
+        const float4 ar = *reinterpret_cast<const float4*>(sG + (size_t)i * SG_LD + wb);
+        const float4 az = *reinterpret_cast<const float4*>(sG + (size_t)(Uc + i) * SG_LD + wb);
+        const float4 an = *reinterpret_cast<const float4*>(sG + (size_t)(2 * Uc + i) * SG_LD + wb);
+        const float arr[4] = {ar.x, ar.y, ar.z, ar.w}, azz[4] = {az.x, az.y, az.z, az.w}, ann[4] = {an.x, an.y, an.z, an.w};
+        float rr[4], zz[4], nv[4], hv_[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          float r = sigm(gr[w] + arr[w] + bhr);
+          float z = sigm(gz[w] + azz[w] + bhz);
+          float hn = ann[w] + bhn;
+          float nn = tanh_fast(gn[w] + r * hn);
+          h[w] = (1.f - z) * nn + z * h[w];
+          rr[w] = r; zz[w] = z; nv[w] = nn; hv_[w] = hn;
+        }
+        if (t + 1 < n) {
+          const uint32_t p0 = pack_h2(h[0], h[1]), p1 = pack_h2(h[2], h[3]);
+          const uint32_t dst = sB_addr + (uint32_t)(((t + 1) & 1) * KC * LBO_B) + hoff;
+          for (int r = 0; r < CS; ++r) st_cluster_v2(mapa(dst, (uint32_t)r), p0, p1);
+        }
+        if (out_p) {
+#pragma unroll
+          for (int w = 0; w < 4; ++w)
+            if (w < nvalid_w) out_p[((size_t)w * n + t) * H] = h[w];
+        }
+        if (gt_p) {
+          float4* gq = reinterpret_cast<float4*>(gt_p + (size_t)t * gt_step);
+          gq[0] = make_float4(rr[0], rr[1], rr[2], rr[3]);
+          gq[(size_t)H * 4] = make_float4(zz[0], zz[1], zz[2], zz[3]);
+          gq[(size_t)2 * H * 4] = make_float4(nv[0], nv[1], nv[2], nv[3]);
+          gq[(size_t)3 * H * 4] = make_float4(hv_[0], hv_[1], hv_[2], hv_[3]);
+        }
+      }
+      named_bar_sync(2, EPI_THREADS);          // staging buffer may be overwritten by the next drain
+      if (t + 1 < n) {
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0)
+          for (int r = 0; r < CS; ++r) mbar_arrive_cluster(mapa(hbar_addr, (uint32_t)r));
+      }
+    }
+    if (valid && P.h_last) {
+#pragma unroll
+      for (int w = 0; w < 4; ++w)
+        if (w < nvalid_w) P.h_last[(size_t)(b0 + wb + w) * H + u] = h[w];
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // no CTA leaves while peers may still touch its shared memory
+  if (warp == 8) tc::tmem_dealloc(tbase, 32);
+}
+
+// ==========================================================================================================
+// BPTT
+// ==========================================================================================================
+struct ClBwdParams {
+  const float* gates; const float* out; const float* w_hh;
+  const float* dout; const float* dh_last;
+  const unsigned int* gmax_bits;
+  float* dgi; float* dghn;
+  int B, n, H, CS, Uc;
+};
+
+static size_t cl_bwd_smem(int H) {
+  int Kp = (3 * H + 15) & ~15, KC = Kp / 8;
+  return (size_t)KC * 64 * 16 + 2 * (size_t)KC * LBO_B + (size_t)64 * SG_LD * 4 + 128;
+}
+
+__global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int H = P.H, G = 3 * H, n = P.n, CS = P.CS, Uc = P.Uc;
+  const int Kp = (G + 15) & ~15, KC = Kp / 8;
+  const int lboA = 64 * 16;
+  uint8_t* sA = smem_raw;                                   // [KC][64 rows][16 B] : W_hh^T rows of this CTA's units
+  uint8_t* sB = sA + (size_t)KC * lboA;                     // [2][KC][256 B]      : dgh (all gates, 16 windows)
+  float* sG = reinterpret_cast<float*>(sB + 2 * (size_t)KC * LBO_B);     // [64][SG_LD]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + 64 * SG_LD);
+  uint64_t* acc_bar = bars;
+  uint64_t* h_bar = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  const int tile = blockIdx.x / CS, b0 = tile * NB;
+  const int u0 = rank * Uc, nu = max(0, min(Uc, H - u0));
+
+  for (int idx = tid; idx < 64 * Kp; idx += CL_THREADS) {
+    int g = idx >> 6, i = idx & 63;                         // i fastest: coalesced reads of W_hh rows
+    float v = (i < nu && g < G) ? __ldg(P.w_hh + (size_t)g * H + u0 + i) : 0.f;
+    *reinterpret_cast<__half*>(sA + (size_t)(g >> 3) * lboA + (size_t)i * 16 + (g & 7) * 2) = __float2half_rn(v);
+  }
+  for (int idx = tid; idx < (2 * KC * LBO_B) / 4; idx += CL_THREADS) reinterpret_cast<uint32_t*>(sB)[idx] = 0u;
+  if (tid == 0) {
+    tc::mbar_init(acc_bar, 1);
+    tc::mbar_init(h_bar, CS * (EPI_THREADS / 32));
+    tc::fence_mbar_init();
+  }
+  if (warp == 8) tc::tmem_alloc(tmem_slot, 32);
+  fence_proxy_async_all();
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc::tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == 8) {
+    const uint32_t idesc = tc::make_idesc_f16(64, NB, 0, /*b_mn_major=*/1);
+    const uint64_t ad0 = tc::make_smem_desc(tc::smem_u32(sA), lboA, 128);
+    const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
+    const uint32_t ainc = (uint32_t)(2 * lboA) >> 4, binc = (uint32_t)(2 * LBO_B) >> 4;
+    const int nkc = Kp / 16;
+    for (int it = 0; it < n - 1; ++it) {
+      mbar_wait_cluster(h_bar, it & 1);
+      fence_proxy_async_all();
+      tc::tc_fence_after();
+      const uint64_t bd0 = tc::make_smem_desc(tc::smem_u32(sB) + (uint32_t)((it & 1) * KC * LBO_B), LBO_B, SBO_B);
+      uint32_t alo = alo0, blo = (uint32_t)bd0;
+      const uint32_t bhi = (uint32_t)(bd0 >> 32);
+      for (int kc = 0; kc < nkc; ++kc) {
+        if (tc::elect_one()) tc::mma_f16_ss_lohi(tbase, alo, ahi, blo, bhi, idesc, kc > 0 ? 1u : 0u);
+        alo += ainc; blo += binc;
+      }
+      if (tc::elect_one()) tc::mma_commit(acc_bar);
+      __syncwarp();
+    }
+  } else {
+    const int i = tid >> 2, wq = tid & 3, wb = 4 * wq;
+    const bool valid = i < nu;
+    const int u = u0 + i;
+    const float gmax = __uint_as_float(*P.gmax_bits);
+    const float scale = gmax > 0.f ? exp2f(floorf(log2f(64.f / gmax))) : 1.f;
+    const float inv_scale = 1.f / scale;
+    float dhz[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t woff = (uint32_t)(wq >> 1) * SBO_B + (uint32_t)(wq & 1) * 8;
+    const uint32_t off0 = (uint32_t)(u >> 3) * LBO_B + (uint32_t)(u & 7) * 16 + woff;
+    const uint32_t off1 = (uint32_t)((H + u) >> 3) * LBO_B + (uint32_t)((H + u) & 7) * 16 + woff;
+    const uint32_t off2 = (uint32_t)((2 * H + u) >> 3) * LBO_B + (uint32_t)((2 * H + u) & 7) * 16 + woff;
+    const uint32_t sB_addr = tc::smem_u32(sB), hbar_addr = tc::smem_u32(h_bar);
+    const size_t gt_step = (size_t)4 * H * 16, gi_step = (size_t)G * 16, gn_step = (size_t)H * 16;
+    const float* gt_p = valid ? P.gates + ((size_t)tile * n * 4 * H + u) * 16 + wb : nullptr;
+    float* dgi_p = valid ? P.dgi + ((size_t)tile * n * G + u) * 16 + wb : nullptr;
+    float* dgn_p = valid ? P.dghn + ((size_t)tile * n * H + u) * 16 + wb : nullptr;
+    const int nvalid_w = max(0, min(4, P.B - (b0 + wb)));
+    const size_t row0 = (size_t)(b0 + wb) * n;
+    // M = 64 accumulator: row i lives in TMEM lane 32*(i/16) + i%16  -> warp q drains rows 16q .. 16q+15
+    const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+
+    for (int t = n - 1; t >= 0; --t) {
+      const int it = n - 1 - t;
+      float dh[4], hp[4], r[4], z[4], nn[4], hn[4];
+      if (valid) {
+        const float4* gq = reinterpret_cast<const float4*>(gt_p + (size_t)t * gt_step);
+        float4 a = __ldg(gq), c = __ldg(gq + (size_t)H * 4), e = __ldg(gq + (size_t)2 * H * 4), f = __ldg(gq + (size_t)3 * H * 4);
+        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+        z[0] = c.x; z[1] = c.y; z[2] = c.z; z[3] = c.w;
+        nn[0] = e.x; nn[1] = e.y; nn[2] = e.z; nn[3] = e.w;
+        hn[0] = f.x; hn[1] = f.y; hn[2] = f.z; hn[3] = f.w;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          float v = 0.f, p = 0.f;
+          if (w < nvalid_w) {
+            size_t o = (row0 + (size_t)w * n + t) * H + u;
+            if (P.dout) v = __ldg(P.dout + o);
+            if (it == 0 && P.dh_last) v += __ldg(P.dh_last + (size_t)(b0 + wb + w) * H + u);
+            if (t > 0) p = __ldg(P.out + o - H);
+          }
+          dh[w] = v; hp[w] = p;
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { dh[w] = 0.f; hp[w] = 0.f; r[w] = 0.f; z[w] = 0.f; nn[w] = 0.f; hn[w] = 0.f; }
+      }
+      if (it > 0) {
+        if (warp < 4) {
+          tc::mbar_wait(acc_bar, (it - 1) & 1);
+          tc::tc_fence_after();
+          float v[16];
+          tc::tmem_ld16(tlane, v);
+          tc::tmem_ld_wait();
+          if (lane < 16) {
+            float4* dst = reinterpret_cast<float4*>(sG + (size_t)(warp * 16 + lane) * SG_LD);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);   dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            dst[2] = make_float4(v[8], v[9], v[10], v[11]); dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+          }
+          tc::tc_fence_before();
+        }
+        named_bar_sync(1, EPI_THREADS);
+        if (valid) {
+          const float4 acc = *reinterpret_cast<const float4*>(sG + (size_t)i * SG_LD + wb);
+          dh[0] += dhz[0] + acc.x * inv_scale; dh[1] += dhz[1] + acc.y * inv_scale;
+          dh[2] += dhz[2] + acc.z * inv_scale; dh[3] += dhz[3] + acc.w * inv_scale;
+        }
+      }
+      if (valid) {
+        float dpr[4], dpz[4], dpn[4], dgn[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          float d = dh[w];
+          float dn = d * (1.f - z[w]);
+          float dz = d * (hp[w] - nn[w]);
+          dpn[w] = dn * (1.f - nn[w] * nn[w]);
+          dpz[w] = dz * z[w] * (1.f - z[w]);
+          dpr[w] = dpn[w] * hn[w] * r[w] * (1.f - r[w]);
+          dgn[w] = dpn[w] * r[w];
+          dhz[w] = d * z[w];
+        }
+        float4* q4 = reinterpret_cast<float4*>(dgi_p + (size_t)t * gi_step);
+        q4[0] = make_float4(dpr[0], dpr[1], dpr[2], dpr[3]);
+        q4[(size_t)H * 4] = make_float4(dpz[0], dpz[1], dpz[2], dpz[3]);
+        q4[(size_t)2 * H * 4] = make_float4(dpn[0], dpn[1], dpn[2], dpn[3]);
+        *reinterpret_cast<float4*>(dgn_p + (size_t)t * gn_step) = make_float4(dgn[0], dgn[1], dgn[2], dgn[3]);
+        if (t > 0) {
+          const uint32_t buf = sB_addr + (uint32_t)((it & 1) * KC * LBO_B);
+          const uint32_t a0 = pack_h2(sat_h(dpr[0] * scale), sat_h(dpr[1] * scale)), a1 = pack_h2(sat_h(dpr[2] * scale), sat_h(dpr[3] * scale));
+          const uint32_t c0 = pack_h2(sat_h(dpz[0] * scale), sat_h(dpz[1] * scale)), c1 = pack_h2(sat_h(dpz[2] * scale), sat_h(dpz[3] * scale));
+          const uint32_t e0 = pack_h2(sat_h(dgn[0] * scale), sat_h(dgn[1] * scale)), e1 = pack_h2(sat_h(dgn[2] * scale), sat_h(dgn[3] * scale));
+          for (int rr = 0; rr < CS; ++rr) {
+            st_cluster_v2(mapa(buf + off0, (uint32_t)rr), a0, a1);
+            st_cluster_v2(mapa(buf + off1, (uint32_t)rr), c0, c1);
+            st_cluster_v2(mapa(buf + off2, (uint32_t)rr), e0, e1);
+          }
+        }
+      }
+      if (it > 0) named_bar_sync(2, EPI_THREADS);
+      if (t > 0) {
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0)
+          for (int rr = 0; rr < CS; ++rr) mbar_arrive_cluster(mapa(hbar_addr, (uint32_t)rr));
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) tc::tmem_dealloc(tbase, 32);
+}
+
+__global__ void absmax2_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, long long nb,
+                               unsigned int* __restrict__ out_bits) {
+  float m = 0.f;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  if (a) for (long long j = i; j < na; j += stride) m = fmaxf(m, fabsf(a[j]));
+  if (b) for (long long j = i; j < nb; j += stride) m = fmaxf(m, fabsf(b[j]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+
+template <class Kern, class Params>
+static int launch_cluster(Kern kern, const Params& P, int nblocks, int cs, size_t smem, cudaStream_t s) {
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nblocks);
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, P);
+  if (e != cudaSuccess) { mtadgat_set_error("cluster launch failed: %s", cudaGetErrorString(e)); return MTADGAT_ERR_CUDA; }
+  MG_COUNT_LAUNCH();
+  return MTADGAT_OK;
+}
+
+}  // namespace
+
+int mtadgat_gru_cl_supported(int H, int Hs_rep) {
+  ClGeom g;
+  if (!cl_geom(H, g)) return 0;
+  return cl_fwd_smem(H, Hs_rep) <= 220 * 1024 && cl_bwd_smem(H) <= 220 * 1024;
+}
+
+int mtadgat_gru_cl_fwd_launch(const float* gi_t, const float* S, const float* hsrc, const float* b_ih, int J, int Hs,
+                              const float* w_hh, const float* b_hh, float* out, float* h_last, float* gates_t, int B,
+                              int n, int H, cudaStream_t s) {
+  ClGeom g;
+  if (!cl_geom(H, g)) { mtadgat_set_error("gru_cl_fwd: unsupported hidden size %d", H); return MTADGAT_ERR_UNSUPPORTED; }
+  ClFwdParams P;
+  P.gi = gi_t; P.S = S; P.hsrc = hsrc; P.b_ih = b_ih; P.J = J; P.Hs = Hs; P.w_hh = w_hh; P.b_hh = b_hh;
+  P.out = out; P.h_last = h_last; P.gates = gates_t; P.B = B; P.n = n; P.H = H; P.CS = g.CS; P.Uc = g.Uc;
+  return launch_cluster(gru_cl_fwd_kernel, P, cdiv(B, NB) * g.CS, g.CS, cl_fwd_smem(H, gi_t ? 0 : Hs), s);
+}
+
+int mtadgat_gru_cl_bwd_launch(const float* gates_t, const float* out, const float* w_hh, const float* dout,
+                              const float* dh_last, unsigned int* gmax_bits, float* dgi_t, float* dghn_t, int B, int n,
+                              int H, cudaStream_t s) {
+  ClGeom g;
+  if (!cl_geom(H, g)) { mtadgat_set_error("gru_cl_bwd: unsupported hidden size %d", H); return MTADGAT_ERR_UNSUPPORTED; }
+  cudaMemsetAsync(gmax_bits, 0, sizeof(unsigned int), s);
+  absmax2_kernel<<<148, 256, 0, s>>>(dout, dout ? (long long)B * n * H : 0, dh_last, dh_last ? (long long)B * H : 0, gmax_bits);
+  MG_COUNT_LAUNCH();
+  ClBwdParams P;
+  P.gates = gates_t; P.out = out; P.w_hh = w_hh; P.dout = dout; P.dh_last = dh_last; P.gmax_bits = gmax_bits;
+  P.dgi = dgi_t; P.dghn = dghn_t; P.B = B; P.n = n; P.H = H; P.CS = g.CS; P.Uc = g.Uc;
+  return launch_cluster(gru_cl_bwd_kernel, P, cdiv(B, NB) * g.CS, g.CS, cl_bwd_smem(H), s);
+}

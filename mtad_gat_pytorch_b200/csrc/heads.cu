@@ -16,25 +16,18 @@ struct StLinear {
   }
 };
 
-// dpre[m][o] = dy * mult * (act ? y>0 : 1)
-struct DpreLin {
-  const float* dy; const float* y; int O; int act; float p, inv_keep; const unsigned long long* seed; uint32_t stream;
-  __device__ __forceinline__ float get(int m, int o) const {
-    long long i = (long long)m * O + o;
-    float v = __ldg(dy + i);
-    if (act == ACT_RELU && !(__ldg(y + i) > 0.f)) return 0.f;
-    if (p > 0.f) v *= dropout_mult(seed, stream, (unsigned long long)i, p, inv_keep);
-    return v;
-  }
-};
-struct DpreA : DpreLin {   // A(m, kk=o)
-  static constexpr bool fast_second = true;
-  __device__ __forceinline__ float operator()(int, int m, int o) const { return get(m, o); }
-};
-struct DpreAT : DpreLin {  // A(m=o, kk=row)
-  static constexpr bool fast_second = false;
-  __device__ __forceinline__ float operator()(int, int o, int m) const { return get(m, o); }
-};
+// dpre[i] = dy[i] * dropout multiplier * (act ? y>0 : 1), materialised once so the three backward GEMMs stream
+// plain fp32 (the Philox recomputation is ~100 instructions per element -- too costly inside a GEMM loader)
+__global__ void dpre_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dpre,
+                            long long numel, int act, float p, float inv_keep, const unsigned long long* seed,
+                            uint32_t stream) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= numel) return;
+  float v = __ldg(dy + i);
+  if (act == ACT_RELU && !(__ldg(y + i) > 0.f)) v = 0.f;
+  else if (p > 0.f) v *= dropout_mult(seed, stream, (unsigned long long)i, p, inv_keep);
+  dpre[i] = v;
+}
 
 }  // namespace
 
@@ -53,22 +46,29 @@ extern "C" int mtadgat_linear_fwd(const float* x, const float* w, const float* b
 }
 
 extern "C" int mtadgat_linear_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx,
-                                  int dx_accumulate, float* dw, float* db, int M, int I, int O, int act, float p_drop,
-                                  const unsigned long long* seed, unsigned int rng_stream, void* stream) {
+                                  int dx_accumulate, float* dw, float* db, float* scratch, int M, int I, int O, int act,
+                                  float p_drop, const unsigned long long* seed, unsigned int rng_stream, void* stream) {
   MG_CHECK_ARG(x && w && y && dy && dw && db, "linear_bwd: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
-  const float inv_keep = 1.f / (1.f - p_drop);
-  DpreA A; A.dy = dy; A.y = y; A.O = O; A.act = act; A.p = p_drop; A.inv_keep = inv_keep; A.seed = seed; A.stream = rng_stream;
-  DpreAT At; At.dy = dy; At.y = y; At.O = O; At.act = act; At.p = p_drop; At.inv_keep = inv_keep; At.seed = seed; At.stream = rng_stream;
+  const float* src = dy;
+  if (act != ACT_NONE || p_drop > 0.f) {
+    MG_CHECK_ARG(scratch, "linear_bwd: scratch (M*O floats) required when an activation or dropout is fused");
+    long long numel = (long long)M * O;
+    dpre_kernel<<<cdiv(numel, 256), 256, 0, s>>>(dy, y, scratch, numel, act, p_drop, 1.f / (1.f - p_drop), seed, rng_stream);
+    MG_COUNT_LAUNCH();
+    src = scratch;
+  }
   if (dx) {
-    // dx = dpre W : B(kk=o, n=i) = w[o*I + i]
-    launch_gemm_batched(1, M, I, O, A, Strided2<true>{w, 0, I, 1}, StStrided{dx, 0, I, 1, nullptr, ACT_NONE, dx_accumulate}, s);
+    // dx = dpre W : A(m,kk=o) = dpre[m*O+o] ; B(kk=o, n=i) = w[o*I + i]
+    launch_gemm_batched(1, M, I, O, Strided2<true>{src, 0, O, 1}, Strided2<true>{w, 0, I, 1},
+                        StStrided{dx, 0, I, 1, nullptr, ACT_NONE, dx_accumulate}, s);
   }
   MG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)O * I, s));
   MG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)O, s));
-  // dw[o][i] = sum_m dpre[m][o] x[m][i]
-  launch_gemm_splitk(O, I, M, At, Strided2<true>{x, 0, I, 1}, StStrided{dw, 0, I, 1, nullptr, ACT_NONE, 0}, s);
-  launch_colsum(M, O, A, db, s);
+  // dw[o][i] = sum_m dpre[m][o] x[m][i] : A(m=o, kk=row) = dpre[row*O + o]
+  launch_gemm_splitk(O, I, M, Strided2<false>{src, 0, 1, O}, Strided2<true>{x, 0, I, 1},
+                     StStrided{dw, 0, I, 1, nullptr, ACT_NONE, 0}, s);
+  launch_colsum(M, O, Strided2<true>{src, 0, O, 1}, db, s);
   MG_CHECK_LAUNCH("linear_bwd");
   return MTADGAT_OK;
 }

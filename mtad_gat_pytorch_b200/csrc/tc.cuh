@@ -62,6 +62,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// ... x 8 consecutive columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors -------------------------------------------------------------------------------------------
@@ -77,8 +87,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t start_addr, uint32_t
   return d;                      // layout_type_ (bits 61..63) = 0: SWIZZLE_NONE
 }
 // Instruction descriptor for kind::f16: A,B = F16 (format 0) or BF16 (1), D = F32, both operands K-major.
-__device__ __host__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int ab_format) {
+// b_mn_major = 1: the B operand is stored N-contiguous ("MN-major") instead of K-contiguous.
+__device__ __host__ __forceinline__ uint32_t make_idesc_f16(int M, int N, int ab_format, int b_mn_major = 0) {
   uint32_t d = 0;
+  d |= (uint32_t)(b_mn_major & 1) << 16;     // b_major
   d |= 1u << 4;                              // c_format = F32
   d |= (uint32_t)(ab_format & 7) << 7;       // a_format
   d |= (uint32_t)(ab_format & 7) << 10;      // b_format
@@ -106,6 +118,16 @@ __device__ __forceinline__ void mma_f16_ss_lohi(uint32_t d_tmem, uint32_t alo, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}"
       ::"r"(d_tmem), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a converged warp (for warp-uniform issue loops: descriptor arithmetic stays on the uniform datapath)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

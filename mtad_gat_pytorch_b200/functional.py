@@ -243,8 +243,9 @@ class LinearFn(torch.autograd.Function):
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = torch.empty_like(w)
         db = torch.empty(O, dtype=torch.float32, device=x.device)
+        scratch = _empty(M * O, x) if (act or p > 0.0) else None
         check(lib.mtadgat_linear_bwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dx), 0,
-                                     dw.data_ptr(), db.data_ptr(), M, I, O, act, p,
+                                     dw.data_ptr(), db.data_ptr(), _ptr(scratch), M, I, O, act, p,
                                      seed_t.data_ptr() if has_seed else None, rng_stream, _stream()))
         return dx, dw, db, None, None, None, None
 
@@ -252,11 +253,22 @@ class LinearFn(torch.autograd.Function):
 def set_gru_impl(name):
     """'tc' (default): persistent tcgen05/TMEM recurrence, fp16 operands, fp32 accumulate + fp32 state;
     'fp32': SIMT fp32 recurrence."""
-    check(lib.mtadgat_set_gru_impl({"fp32": 0, "tc": 1}[name]))
+    check(lib.mtadgat_set_gru_impl({"fp32": 0, "tc": 1, "tc1": 2}[name]))
+
+
+def set_gemm_impl(name):
+    """'tc' (default): tcgen05 3xTF32 GEMMs; 'fp32': SIMT fp32 GEMMs."""
+    check(lib.mtadgat_set_gemm_impl({"fp32": 0, "tc": 1}[name]))
+
+
+def set_mode(name):
+    """'tc': tensor cores everywhere (default); 'fp32': every kernel on the fp32 SIMT path."""
+    set_gemm_impl("fp32" if name == "fp32" else "tc")
+    set_gru_impl(name)
 
 
 def get_gru_impl():
-    return {0: "fp32", 1: "tc"}[lib.mtadgat_get_gru_impl()]
+    return {0: "fp32", 1: "tc", 2: "tc1"}[lib.mtadgat_get_gru_impl()]
 
 
 def launch_count():

@@ -1,5 +1,6 @@
 """`MTAD_GAT` with the reference's constructor / forward signature (reference mtad_gat.py:37-79), running the
 per-window pipeline on the sm_100a kernels in libmtadgat.so."""
+import torch
 import torch.nn as nn
 
 from . import functional as F
@@ -23,6 +24,18 @@ class MTAD_GAT(nn.Module):
         self.forecasting_model = Forecasting_Model(gru_hid_dim, forecast_hid_dim, out_dim, forecast_n_layers, dropout)
         self.recon_model = ReconstructionModel(window_size, gru_hid_dim, recon_hid_dim, out_dim, recon_n_layers, dropout)
         self._dropout = dropout
+        # Run the two independent branch pairs (feature GAT || temporal GAT, forecasting head || reconstruction
+        # decoder) on two CUDA streams: at batch 256 every kernel is far too small to fill 148 SMs on its own.
+        # autograd replays each backward on the stream its forward ran on, so the backward overlaps the same way,
+        # and a CUDA-graph capture of the step records the fork/join as parallel graph branches.
+        self.branch_parallel = True
+        self._side = {}
+
+    def _side_stream(self, device):
+        s = self._side.get(device)
+        if s is None:
+            s = self._side[device] = torch.cuda.Stream(device=device)
+        return s
 
     def _seeded(self):
         return (self.feature_gat, self.temporal_gat, self.gru, self.forecasting_model, self.recon_model.decoder)
@@ -34,11 +47,29 @@ class MTAD_GAT(nn.Module):
             m._step_seed = seed
         try:
             xc = self.conv(x)                                   # mtad_gat.py:67
-            h_feat = self.feature_gat(xc)                       # :68
-            h_temp = self.temporal_gat(xc)                      # :69
-            h_end = self.gru.forward_slices([xc, h_feat, h_temp])   # :71-74 (cat never materialised)
-            predictions = self.forecasting_model(h_end)         # :76
-            recons = self.recon_model(h_end)                    # :77
+            if self.branch_parallel:
+                main, side = torch.cuda.current_stream(x.device), self._side_stream(x.device)
+                side.wait_stream(main)
+                xc.record_stream(side)
+                with torch.cuda.stream(side):
+                    h_feat = self.feature_gat(xc)               # :68
+                h_temp = self.temporal_gat(xc)                  # :69
+                main.wait_stream(side)
+                h_feat.record_stream(main)
+                h_end = self.gru.forward_slices([xc, h_feat, h_temp])   # :71-74 (cat never materialised)
+                side.wait_stream(main)
+                h_end.record_stream(side)
+                with torch.cuda.stream(side):
+                    predictions = self.forecasting_model(h_end)     # :76
+                recons = self.recon_model(h_end)                # :77
+                main.wait_stream(side)
+                predictions.record_stream(main)
+            else:
+                h_feat = self.feature_gat(xc)
+                h_temp = self.temporal_gat(xc)
+                h_end = self.gru.forward_slices([xc, h_feat, h_temp])
+                predictions = self.forecasting_model(h_end)
+                recons = self.recon_model(h_end)
         finally:
             for m in self._seeded():
                 m._step_seed = None

@@ -43,7 +43,7 @@ def test_host_side_queries_need_no_gpu(mg):
     assert lib.mtadgat_rep_J(512, 150) == 2
     assert lib.mtadgat_rep_J(10, 150) == 15
     assert lib.mtadgat_gru_saved_floats(4, 10, 8, 0) == 3 * 8 * 8
-    assert lib.mtadgat_gru_saved_floats(4, 10, 8, 1) == 3 * 8 * 8 + 4 * 10 * 4 * 8
+    assert lib.mtadgat_gru_saved_floats(4, 10, 8, 1) == 3 * 8 * 8 + 16 * 10 * 4 * 8   # windows padded to 16 (tiled layout)
     a = lib.mtadgat_gat_saved_floats(2, 100, 38, 76, 0, 1, 0)
     b = lib.mtadgat_gat_saved_floats(2, 100, 38, 76, 0, 1, 1)
     assert b - a == 2 * 100 * 100                      # attention (B,K,Kp) kept only when gradients are needed

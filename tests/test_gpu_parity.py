@@ -50,9 +50,35 @@ def loss_fn(x, y, preds, recons, td):
 @pytest.fixture(autouse=True)
 def _default_impl():
     import mtad_gat_pytorch_b200 as mg
-    mg.set_gru_impl("tc")
+    mg.set_mode("tc")
     yield
-    mg.set_gru_impl("tc")
+    mg.set_mode("tc")
+
+
+@pytest.mark.parametrize("shape", [(256, 150, 150), (25600, 114, 450), (77, 38, 200), (1000, 266, 38), (33, 16, 16)])
+def test_tc_gemm_3xtf32_linear(shape):
+    """The tcgen05 3xTF32 GEMM behind nn.Linear-shaped stages vs a float64 matmul: fp32-level accuracy."""
+    import mtad_gat_pytorch_b200 as mg
+    from mtad_gat_pytorch_b200 import functional as F
+    M, I, O = shape
+    g = torch.Generator(device="cpu").manual_seed(M + I)
+    x = torch.randn(M, I, generator=g).cuda().requires_grad_(True)
+    w = (torch.randn(O, I, generator=g) / I ** 0.5).cuda().requires_grad_(True)
+    b = torch.randn(O, generator=g).cuda().requires_grad_(True)
+    gy = torch.randn(M, O, generator=g).cuda()
+    ref = x.detach().double() @ w.detach().double().t() + b.detach().double()
+    res = {}
+    for impl in ("fp32", "tc"):
+        mg.set_mode(impl)
+        for t in (x, w, b):
+            t.grad = None
+        y = F.LinearFn.apply(x, w, b, 0, 0.0, None, 0)
+        y.backward(gy)
+        res[impl] = (rel(y, ref.cpu().numpy()), rel(x.grad, (gy.double() @ w.detach().double()).cpu().numpy()),
+                     rel(w.grad, (gy.double().t() @ x.detach().double()).cpu().numpy()),
+                     rel(b.grad, gy.double().sum(0).cpu().numpy()))
+    print(f"[linear {shape}] fp32 {['%.1e' % e for e in res['fp32']]} tc {['%.1e' % e for e in res['tc']]}")
+    assert max(res["tc"]) < 2e-5 and max(res["fp32"]) < 2e-5
 
 
 def test_tcgen05_probe_matches_fp16_matmul():
@@ -60,27 +86,28 @@ def test_tcgen05_probe_matches_fp16_matmul():
     including tiles that start at an arbitrary 8-row boundary and run past the end of the matrix."""
     from mtad_gat_pytorch_b200._lib import lib, check
     g = torch.Generator(device="cpu").manual_seed(0)
-    for (Mtot, K, N, row0) in ((128, 16, 16, 0), (128, 160, 16, 0), (456, 160, 16, 152), (456, 160, 16, 432), (136, 32, 32, 8)):
+    for (Mtot, K, N, row0, bmn) in ((128, 16, 16, 0, 0), (128, 160, 16, 0, 0), (456, 160, 16, 152, 0), (456, 160, 16, 432, 1),
+                                    (136, 32, 32, 8, 0), (128, 16, 16, 0, 1), (152, 464, 16, 0, 1), (136, 32, 32, 8, 1)):
         A = torch.randn(Mtot, K, generator=g).cuda()
         Bm = torch.randn(N, K, generator=g).cuda()
         D = torch.zeros(128, N, device="cuda")
-        check(lib.mtadgat_tc_probe(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), Mtot, row0, K, N,
+        check(lib.mtadgat_tc_probe(A.data_ptr(), Bm.data_ptr(), D.data_ptr(), Mtot, row0, K, N, bmn, 128,
                                    torch.cuda.current_stream().cuda_stream))
         torch.cuda.synchronize()
         rows = min(128, Mtot - row0)
         ref = A[row0:row0 + rows].half().float() @ Bm.half().float().t()
         err = float((D[:rows] - ref).abs().max() / ref.abs().max())
-        print(f"[tc probe Mtot={Mtot} K={K} N={N} row0={row0}] rel err {err:.2e}")
-        assert err < 1e-5, (Mtot, K, N, row0, err)
+        print(f"[tc probe Mtot={Mtot} K={K} N={N} row0={row0} b_mn_major={bmn}] rel err {err:.2e}")
+        assert err < 1e-5, (Mtot, K, N, row0, bmn, err)
 
 
-@pytest.mark.parametrize("impl", ["fp32", "tc"])
+@pytest.mark.parametrize("impl", ["fp32", "tc", "tc1"])
 @pytest.mark.parametrize("name", list(CASES))
 def test_golden_forward_backward(name, impl):
     """Outputs, dx and every parameter gradient vs the fixture the reference produced.
     impl=fp32: SIMT fp32 recurrence (tight bound); impl=tc: tcgen05 recurrence with fp16 operands (the 1e-3 gate)."""
     import mtad_gat_pytorch_b200 as mg
-    mg.set_gru_impl(impl)
+    mg.set_mode(impl)
     tol = TIGHT if impl == "fp32" else TOL
     kwargs, B, td, seed = CASES[name]
     g = np.load(os.path.join(GOLD, name + ".npz"))
@@ -137,7 +164,7 @@ def test_smd_checkpoint_replay(impl):
     """Shipped SMD-1-1 checkpoint + in-tree data: the double forward of prediction.py:55-59 reproduces the
     shipped Forecast_i / Recon_i columns for the first 256 test windows."""
     import mtad_gat_pytorch_b200 as mg
-    mg.set_gru_impl(impl)
+    mg.set_mode(impl)
     g = np.load(os.path.join(GOLD, "smd_1_1_replay.npz"))
     sd = {k[len("param."):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("param.")}
     m = mg.MTAD_GAT(38, 100, 38, forecast_n_layers=3, dropout=0.3)
@@ -188,7 +215,7 @@ def test_extreme_attention_bias_survives_softmax(which):
 def test_variants_vs_oracle(impl):
     """Constructor variants from SURVEY.md §4 at SMD shape (v1, custom embed dims, kernel 5, hidden dims, out_dim=1)."""
     import mtad_gat_pytorch_b200 as mg
-    mg.set_gru_impl(impl)
+    mg.set_mode(impl)
     tol = TIGHT if impl == "fp32" else TOL
     variants = [
         dict(use_gatv2=False),
@@ -230,7 +257,7 @@ def test_dropout_masks_and_train_mode_parity():
     params = orc.make_params(cfg, seed=40, dtype=np.float64)
     B = 5
     x, y = inputs_for(cfg, B, 40)
-    mg.set_gru_impl("fp32")
+    mg.set_mode("fp32")
     m = build(kwargs, params, train=True)
     mg.manual_seed(1234)
     # what MTAD_GAT.forward will draw: advance + copy
@@ -302,7 +329,7 @@ def test_full_size_c2_backward_properties():
     """C2 (k=38,n=100,B=256) backward: the backward map is linear in the output gradient and parameter
     gradients are sums over windows -- checked exactly as split-batch consistency and linearity."""
     import mtad_gat_pytorch_b200 as mg
-    mg.set_gru_impl("fp32")
+    mg.set_mode("fp32")
     kwargs, cfg, params, m = _full_size_model(38, 100, 38, 51)
     B = 256
     rng = np.random.default_rng(10)
@@ -359,7 +386,7 @@ def test_gru_layer_vs_torch_fp32_reference():
     """Floating-point kernel vs a plain PyTorch fp32 reference of the same op (nn.GRU on the GPU)."""
     import mtad_gat_pytorch_b200 as mg
     torch.manual_seed(0)
-    mg.set_gru_impl("fp32")
+    mg.set_mode("fp32")
     B, n, I, H = 9, 33, 21, 50
     layer = mg.GRULayer(I, H, 1, 0.0).cuda()
     x = torch.randn(B, n, I, device="cuda", requires_grad=True)
