@@ -94,12 +94,13 @@ int mtadgat_linear_bwd(const float* x, const float* w, const float* y, const flo
  *      128 x N x K product through the same shared-memory operand layout (diagnostic / unit test). ---- */
 int mtadgat_set_gru_impl(int impl);
 int mtadgat_get_gru_impl(void);
-/* GEMM-shaped stages (conv, projections, heads, weight gradients): 1 (default) = tcgen05 kind::tf32 with the 3xTF32
- * split (fp32-level accuracy), 0 = SIMT fp32. */
+/* GEMM-shaped stages (conv, projections, heads, weight gradients): 1 (default) = tcgen05 kind::f16 on bf16 hi/lo splits
+ * (bf16x3, ~1e-5 relative), 0 = SIMT fp32. */
 int mtadgat_set_gemm_impl(int impl);
 int mtadgat_get_gemm_impl(void);
 int mtadgat_tc_probe(const float* A, const float* Bm, float* D, int Mtot, int row0, int K, int N, int b_mn_major,
                      int mma_m, void* stream);
+void mtadgat_gru_debug_buffer(long long* dev_ptr);   /* optional: 16 int64 per-phase cycle counters of the cluster GRU */
 int mtadgat_tc_mma_bench(int ntiles, int kchunks, int M, int N, int iters, int row_stride, int nissuers, int mode,
                          long long* out_cycles, void* stream);
 

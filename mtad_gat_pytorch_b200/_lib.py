@@ -45,6 +45,7 @@ SIGNATURES = {
     "mtadgat_set_gru_impl": (_I, [_I]),
     "mtadgat_get_gru_impl": (_I, []),
     "mtadgat_tc_probe": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "mtadgat_gru_debug_buffer": (None, [_P]),
     "mtadgat_tc_mma_bench": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "mtadgat_dropout_mask": (_I, [_P, _LL, _F, _P, _U, _P]),
     "mtadgat_seed_advance": (_I, [_P, _P]),

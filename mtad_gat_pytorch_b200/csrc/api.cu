@@ -6,7 +6,7 @@
 
 static thread_local char g_err[512] = "";
 unsigned long long g_mtadgat_launches = 0;
-int g_mtadgat_gemm_impl = 1;   // 1 = tcgen05 3xTF32 GEMMs (tc_gemm.cuh), 0 = SIMT fp32 (gemm.cuh)
+int g_mtadgat_gemm_impl = 1;   // 1 = tcgen05 bf16x3 GEMMs (tc_gemm.cuh), 0 = SIMT fp32 (gemm.cuh)
 
 void mtadgat_set_error(const char* fmt, ...) {
   va_list ap;
@@ -20,7 +20,7 @@ extern "C" int mtadgat_abi_version(void) { return MTADGAT_ABI_VERSION; }
 extern "C" unsigned long long mtadgat_launch_count(void) { return g_mtadgat_launches; }
 extern "C" void mtadgat_reset_launch_count(void) { g_mtadgat_launches = 0; }
 extern "C" int mtadgat_set_gemm_impl(int impl) {
-  MG_CHECK_ARG(impl == 0 || impl == 1, "set_gemm_impl: 0 (SIMT fp32) or 1 (tcgen05 3xTF32)");
+  MG_CHECK_ARG(impl == 0 || impl == 1, "set_gemm_impl: 0 (SIMT fp32) or 1 (tcgen05 bf16x3)");
   g_mtadgat_gemm_impl = impl;
   return MTADGAT_OK;
 }

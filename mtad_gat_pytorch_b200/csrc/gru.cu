@@ -252,20 +252,23 @@ __global__ void rep_build_S_kernel(const float* __restrict__ w_ih, int n, int Hs
   for (int c = clo; c < chi; ++c) acc += w_ih[(long long)g * Hs + c];
   S[idx] = acc;
 }
-// dW_ih[g][c] = sum_t dS[t][(t*Hs+c)//n - m0[t]][g]
+// dW_ih[g][c] = sum_t dS[t][(t*Hs+c)//n - m0[t]][g];   (t*Hs+c)//n - (t*Hs)//n = ((t*Hs)%n + c)//n, tracked incrementally
 __global__ void rep_dw_kernel(const float* __restrict__ dS, int n, int Hs, int G, int J, float* __restrict__ dw_ih) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= G * Hs) return;
   int c = idx % Hs, g = idx / Hs;
   float acc = 0.f;
+  int rem = 0;                                  // (t*Hs) % n
   for (int t = 0; t < n; ++t) {
-    long long base = (long long)t * Hs;
-    int j = (int)((base + c) / n) - (int)(base / n);
-    acc += dS[((long long)t * J + j) * G + g];
+    int v = rem + c, j = 0;
+    while (v >= n) { v -= n; ++j; }
+    acc += __ldg(dS + ((long long)t * J + j) * G + g);
+    rem += Hs;
+    while (rem >= n) rem -= n;
   }
   dw_ih[idx] = acc;
 }
-// dS[t][j][g] = sum_b dgi[b,t,g] * hsrc[b, m0[t]+j]        (dgi window-tiled)
+// dS[t][j][g] = sum_b dgi[b,t,g] * hsrc[b, m0[t]+j]        (dgi window-tiled: 16 windows per 64-byte line)
 __global__ void rep_dS_kernel(const float* __restrict__ dgi_t, const float* __restrict__ hsrc, int B, int n, int Hs,
                               int G, int J, float* __restrict__ dS) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -273,16 +276,29 @@ __global__ void rep_dS_kernel(const float* __restrict__ dgi_t, const float* __re
   int g = idx % G, j = (idx / G) % J, t = idx / (G * J);
   int m = (int)(((long long)t * Hs) / n) + j;
   float acc = 0.f;
-  if (m < Hs)
-    for (int b = 0; b < B; ++b) acc += dgi_t[tiled_idx(b, t, g, n, G)] * hsrc[(long long)b * Hs + m];
+  if (m < Hs) {
+    const int ntiles = (B + 15) >> 4;
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const float4* p = reinterpret_cast<const float4*>(dgi_t + (((size_t)tile * n + t) * G + g) * 16);
+      float4 a = __ldg(p), b4 = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+      const float v[16] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+      const int b0 = tile * 16;
+#pragma unroll
+      for (int w = 0; w < 16; ++w)
+        if (b0 + w < B) acc = fmaf(v[w], __ldg(hsrc + (size_t)(b0 + w) * Hs + m), acc);
+    }
+  }
   dS[idx] = acc;
 }
-// dhsrc[b][m] (+)= sum_{t,j: m0[t]+j == m} sum_g dgi[b,t,g] S[t][j][g]      one warp per (b,m)
+// dhsrc[b][m] (+)= sum_{t,j: m0[t]+j == m} sum_g dgi[b,t,g] S[t][j][g]
+// one warp per (tile, m): lane = (g parity, window) so every load of the tiled dgi is a full 64-byte line
 __global__ void rep_dh_kernel(const float* __restrict__ dgi_t, const float* __restrict__ S, int B, int n, int Hs, int G,
                               int J, float* __restrict__ dh, int accumulate) {
+  const int ntiles = (B + 15) >> 4;
   int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (wid >= B * Hs) return;
-  int m = wid % Hs, b = wid / Hs;
+  if (wid >= ntiles * Hs) return;
+  const int m = wid % Hs, tile = wid / Hs;
+  const int w = lane & 15, gh = lane >> 4;
   float acc = 0.f;
   int tlo = (int)(((long long)max(m - J + 1, 0) * n) / Hs);
   int thi = (int)min((long long)n - 1, (((long long)(m + 1) * n) / Hs));
@@ -290,10 +306,15 @@ __global__ void rep_dh_kernel(const float* __restrict__ dgi_t, const float* __re
     int j = m - (int)(((long long)t * Hs) / n);
     if (j < 0 || j >= J) continue;
     const float* s = S + ((long long)t * J + j) * G;
-    for (int g = lane; g < G; g += 32) acc = fmaf(dgi_t[tiled_idx(b, t, g, n, G)], s[g], acc);
+    const float* d = dgi_t + (((size_t)tile * n + t) * G) * 16 + w;
+    for (int g = gh; g < G; g += 2) acc = fmaf(__ldg(d + (size_t)g * 16), __ldg(s + g), acc);
   }
-  acc = warp_sum(acc);
-  if (lane == 0) dh[wid] = accumulate ? dh[wid] + acc : acc;
+  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+  const int b = tile * 16 + w;
+  if (gh == 0 && b < B) {
+    float* q = dh + (size_t)b * Hs + m;
+    *q = accumulate ? *q + acc : acc;
+  }
 }
 
 // ---- fp32 SIMT recurrent forward ------------------------------------------------------------------------
@@ -636,7 +657,7 @@ extern "C" int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const 
   MG_COUNT_LAUNCH();
   rep_dw_kernel<<<cdiv((long long)G * Hs, 256), 256, 0, s>>>(dS, n, Hs, G, J, dw_ih);
   MG_COUNT_LAUNCH();
-  rep_dh_kernel<<<cdiv((long long)B * Hs, 8), 256, 0, s>>>(dgi, S, B, n, Hs, G, J, dh_src, dh_accumulate);
+  rep_dh_kernel<<<cdiv((long long)(Bp / 16) * Hs, 8), 256, 0, s>>>(dgi, S, B, n, Hs, G, J, dh_src, dh_accumulate);
   MG_COUNT_LAUNCH();
   MG_CHECK_LAUNCH("gru_rep_bwd");
   return MTADGAT_OK;

@@ -40,6 +40,27 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank
 __device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t x, uint32_t y) {
   asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
 }
+// asynchronous 8-byte store into a (possibly remote) CTA's shared memory that completes `8` tx-bytes on that CTA's
+// mbarrier: data hand-off and signalling in one instruction, no fences or release-arrives on the producer side
+__device__ __forceinline__ void st_async_v2(uint32_t dst_cluster_addr, uint32_t x, uint32_t y, uint32_t mbar_cluster_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
+               ::"r"(dst_cluster_addr), "r"(x), "r"(y), "r"(mbar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w,
+                                            uint32_t mbar_cluster_addr) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(dst_cluster_addr), "r"(x), "r"(y), "r"(z), "r"(w), "r"(mbar_cluster_addr) : "memory");
+}
+// bulk copy of a contiguous chunk of this CTA's shared memory into a peer CTA's shared memory; completes `bytes`
+// tx-bytes on the peer's mbarrier (ONE barrier update per copy instead of one per 8-byte store)
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                  uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t tx_bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(tx_bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -90,17 +111,19 @@ struct ClFwdParams {
   const float* w_hh; const float* b_hh;
   float* out; float* h_last; float* gates;            // out (B,n,H) | h_last (B,H) | gates tiled (Bp/16,n,4H,16)
   int B, n, H, CS, Uc;
+  long long* dbg;                                     // optional per-phase cycle counters (CTA 0), else nullptr
 };
 
 static size_t cl_fwd_smem(int H, int Hs_rep) {
-  int Kp = (H + 15) & ~15, KC = Kp / 8;
+  ClGeom g; cl_geom(H, g);
+  int Kp = (g.CS * g.Uc + 15) & ~15, KC = Kp / 8;     // K covers every CTA's (padded) unit slot
   return (size_t)KC * 128 * 16 + 2 * (size_t)KC * LBO_B + (size_t)128 * SG_LD * 4 + (size_t)NB * Hs_rep * 4 + 128;
 }
 
 __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int H = P.H, G = 3 * H, n = P.n, CS = P.CS, Uc = P.Uc;
-  const int Kp = (H + 15) & ~15, KC = Kp / 8;
+  const int Kp = (CS * Uc + 15) & ~15, KC = Kp / 8;
   const int lboA = 128 * 16;
   uint8_t* sA = smem_raw;                                   // [KC][128 rows][16 B]
   uint8_t* sB = sA + (size_t)KC * lboA;                     // [2][KC][256 B]
@@ -131,7 +154,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
     }
   if (tid == 0) {
     tc::mbar_init(acc_bar, 1);
-    tc::mbar_init(h_bar, CS * (EPI_THREADS / 32));
+    tc::mbar_init(h_bar, 1);               // per step: the issuer's arrive.expect_tx; h_t arrives as st.async tx-bytes
     tc::fence_mbar_init();
   }
   if (warp == 8) tc::tmem_alloc(tmem_slot, 32);
@@ -149,10 +172,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
     const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
     const uint32_t ainc = (uint32_t)(2 * lboA) >> 4, binc = (uint32_t)(2 * LBO_B) >> 4;
     const int nkc = Kp / 16;
+    const uint32_t tx_bytes = (uint32_t)H * NB * 2;          // the whole h_t (all CTAs' slices) lands in this buffer
+    long long c_wait = 0, c_issue = 0;
     for (int t = 0; t < n; ++t) {
-      if (t > 0) mbar_wait_cluster(h_bar, (t - 1) & 1);
+      long long q0 = clock64();
+      if (t > 0) tc::mbar_wait(h_bar, (t - 1) & 1);
       fence_proxy_async_all();
       tc::tc_fence_after();
+      long long q1 = clock64();
+      c_wait += q1 - q0;
       const uint64_t bd0 = tc::make_smem_desc(tc::smem_u32(sB) + (uint32_t)((t & 1) * KC * LBO_B), LBO_B, SBO_B);
       uint32_t alo = alo0, blo = (uint32_t)bd0;
       const uint32_t bhi = (uint32_t)(bd0 >> 32);
@@ -160,9 +188,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
         if (tc::elect_one()) tc::mma_f16_ss_lohi(tbase, alo, ahi, blo, bhi, idesc, kc > 0 ? 1u : 0u);
         alo += ainc; blo += binc;
       }
-      if (tc::elect_one()) tc::mma_commit(acc_bar);
+      if (tc::elect_one()) {
+        tc::mma_commit(acc_bar);
+        if (t + 1 < n) mbar_arrive_expect_tx(h_bar, tx_bytes);   // arm the phase that receives h_{t+1}
+      }
       __syncwarp();
+      c_issue += clock64() - q1;
     }
+    if (P.dbg && blockIdx.x == 0 && lane == 0) { P.dbg[0] = c_wait / n; P.dbg[1] = c_issue / n; }
   } else {
     // ================= epilogue: thread = (local unit i, 4 windows) =================
     const int i = tid >> 2, wq = tid & 3, wb = 4 * wq;
@@ -184,12 +217,12 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
     const int nvalid_w = max(0, min(4, P.B - (b0 + wb)));
     const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
 
-    for (int t = 0; t < n; ++t) {
-      // input-side pre-activations (independent of the recurrence; issued before the wait)
-      float gr[4], gz[4], gn[4];
+    // input-side pre-activations of step `tt` (independent of the recurrence): software-pipelined one step ahead
+    float gr[4], gz[4], gn[4];
+    auto load_inputs = [&](int tt) {
       if (P.gi) {
         if (valid) {
-          const float4* p = reinterpret_cast<const float4*>(gi_p + (size_t)t * gi_step);
+          const float4* p = reinterpret_cast<const float4*>(gi_p + (size_t)tt * gi_step);
           float4 a = __ldg(p), c = __ldg(p + (size_t)H * 4), e = __ldg(p + (size_t)2 * H * 4);
           gr[0] = a.x; gr[1] = a.y; gr[2] = a.z; gr[3] = a.w;
           gz[0] = c.x; gz[1] = c.y; gz[2] = c.z; gz[3] = c.w;
@@ -199,14 +232,14 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
           for (int w = 0; w < 4; ++w) { gr[w] = 0.f; gz[w] = 0.f; gn[w] = 0.f; }
         }
       } else {
-        const int m0 = (int)(((long long)t * P.Hs) / n);
+        const int m0 = (int)(((long long)tt * P.Hs) / n);
 #pragma unroll
         for (int w = 0; w < 4; ++w) { gr[w] = bir; gz[w] = biz; gn[w] = bin; }
         if (valid)
           for (int j = 0; j < P.J; ++j) {
             int m = m0 + j;
             if (m >= P.Hs) break;
-            const float* sp = P.S + ((size_t)t * P.J + j) * G + u;
+            const float* sp = P.S + ((size_t)tt * P.J + j) * G + u;
             float sr = __ldg(sp), sz = __ldg(sp + H), sn = __ldg(sp + 2 * H);
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
@@ -215,10 +248,17 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
             }
           }
       }
+    };
+    load_inputs(0);
+
+    long long c_acc = 0, c_drain = 0, c_math = 0, c_st = 0, c_tail = 0;
+    for (int t = 0; t < n; ++t) {
+      long long e1 = clock64(), e2 = e1;
       // drain TMEM -> staging (warps 0..3 own the 128 lanes)
       if (warp < 4) {
         tc::mbar_wait(acc_bar, t & 1);
         tc::tc_fence_after();
+        e2 = clock64();
         float v[16];
         tc::tmem_ld16(tlane, v);
         tc::tmem_ld_wait();
@@ -228,12 +268,13 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
         tc::tc_fence_before();
       }
       named_bar_sync(1, EPI_THREADS);
+      long long e3 = clock64(), e4 = e3;
+      float rr[4], zz[4], nv[4], hv_[4];
       if (valid) {
         const float4 ar = *reinterpret_cast<const float4*>(sG + (size_t)i * SG_LD + wb);
         const float4 az = *reinterpret_cast<const float4*>(sG + (size_t)(Uc + i) * SG_LD + wb);
         const float4 an = *reinterpret_cast<const float4*>(sG + (size_t)(2 * Uc + i) * SG_LD + wb);
         const float arr[4] = {ar.x, ar.y, ar.z, ar.w}, azz[4] = {az.x, az.y, az.z, az.w}, ann[4] = {an.x, an.y, an.z, an.w};
-        float rr[4], zz[4], nv[4], hv_[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
           float r = sigm(gr[w] + arr[w] + bhr);
@@ -243,11 +284,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
           h[w] = (1.f - z) * nn + z * h[w];
           rr[w] = r; zz[w] = z; nv[w] = nn; hv_[w] = hn;
         }
-        if (t + 1 < n) {
-          const uint32_t p0 = pack_h2(h[0], h[1]), p1 = pack_h2(h[2], h[3]);
+      }
+      e4 = clock64();
+      if (t + 1 < n) {
+        // hand h_t to every CTA of the cluster with asynchronous stores that complete tx-bytes on the destination's
+        // mbarrier (no fences / release-arrives on the producer side).  Lane pairs (wq, wq^1) merge their 4+4
+        // windows into one 16-byte store to halve the number of barrier updates.
+        const uint32_t p0 = pack_h2(h[0], h[1]), p1 = pack_h2(h[2], h[3]);
+        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, p0, 1), o1 = __shfl_xor_sync(0xffffffffu, p1, 1);
+        if (valid && !(wq & 1)) {
           const uint32_t dst = sB_addr + (uint32_t)(((t + 1) & 1) * KC * LBO_B) + hoff;
-          for (int r = 0; r < CS; ++r) st_cluster_v2(mapa(dst, (uint32_t)r), p0, p1);
+          for (int r = 0; r < CS; ++r) st_async_v4(mapa(dst, (uint32_t)r), p0, p1, o0, o1, mapa(hbar_addr, (uint32_t)r));
         }
+      }
+      long long e5 = clock64();
+      // everything below overlaps with the next step's MMAs
+      if (valid) {
         if (out_p) {
 #pragma unroll
           for (int w = 0; w < 4; ++w)
@@ -261,13 +313,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
           gq[(size_t)3 * H * 4] = make_float4(hv_[0], hv_[1], hv_[2], hv_[3]);
         }
       }
-      named_bar_sync(2, EPI_THREADS);          // staging buffer may be overwritten by the next drain
-      if (t + 1 < n) {
-        fence_proxy_async_all();
-        __syncwarp();
-        if (lane == 0)
-          for (int r = 0; r < CS; ++r) mbar_arrive_cluster(mapa(hbar_addr, (uint32_t)r));
-      }
+      if (t + 1 < n) load_inputs(t + 1);
+      // the staging buffer is rewritten by the next drain only after the next MMA, which needs every thread's
+      // h slice -- i.e. every thread is past its staging reads: no second barrier needed
+      long long e6 = clock64();
+      c_acc += e2 - e1; c_drain += e3 - e2; c_math += e4 - e3; c_st += e5 - e4; c_tail += e6 - e5;
+    }
+    if (P.dbg && blockIdx.x == 0 && tid == 0) {
+      P.dbg[2] = 0; P.dbg[3] = c_acc / n; P.dbg[4] = c_drain / n; P.dbg[5] = c_math / n; P.dbg[6] = c_st / n;
+      P.dbg[7] = c_tail / n; P.dbg[8] = 0; P.dbg[9] = 0; P.dbg[10] = 0; P.dbg[11] = 0;
     }
     if (valid && P.h_last) {
 #pragma unroll
@@ -293,14 +347,16 @@ struct ClBwdParams {
 };
 
 static size_t cl_bwd_smem(int H) {
-  int Kp = (3 * H + 15) & ~15, KC = Kp / 8;
+  ClGeom g; cl_geom(H, g);
+  int Kp = (3 * g.CS * g.Uc + 15) & ~15, KC = Kp / 8;  // gate blocks padded to Hp = CS*Uc so CTA slices are k-group aligned
   return (size_t)KC * 64 * 16 + 2 * (size_t)KC * LBO_B + (size_t)64 * SG_LD * 4 + 128;
 }
 
 __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int H = P.H, G = 3 * H, n = P.n, CS = P.CS, Uc = P.Uc;
-  const int Kp = (G + 15) & ~15, KC = Kp / 8;
+  const int Hp = CS * Uc;                                   // padded gate width: k = gate*Hp + unit
+  const int Kp = (3 * Hp + 15) & ~15, KC = Kp / 8;
   const int lboA = 64 * 16;
   uint8_t* sA = smem_raw;                                   // [KC][64 rows][16 B] : W_hh^T rows of this CTA's units
   uint8_t* sB = sA + (size_t)KC * lboA;                     // [2][KC][256 B]      : dgh (all gates, 16 windows)
@@ -315,14 +371,15 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
   const int u0 = rank * Uc, nu = max(0, min(Uc, H - u0));
 
   for (int idx = tid; idx < 64 * Kp; idx += CL_THREADS) {
-    int g = idx >> 6, i = idx & 63;                         // i fastest: coalesced reads of W_hh rows
-    float v = (i < nu && g < G) ? __ldg(P.w_hh + (size_t)g * H + u0 + i) : 0.f;
-    *reinterpret_cast<__half*>(sA + (size_t)(g >> 3) * lboA + (size_t)i * 16 + (g & 7) * 2) = __float2half_rn(v);
+    int kk = idx >> 6, i = idx & 63;                        // i fastest: coalesced reads of W_hh rows
+    int gate = kk / Hp, uu = kk - gate * Hp;
+    float v = (i < nu && gate < 3 && uu < H) ? __ldg(P.w_hh + ((size_t)gate * H + uu) * H + u0 + i) : 0.f;
+    *reinterpret_cast<__half*>(sA + (size_t)(kk >> 3) * lboA + (size_t)i * 16 + (kk & 7) * 2) = __float2half_rn(v);
   }
   for (int idx = tid; idx < (2 * KC * LBO_B) / 4; idx += CL_THREADS) reinterpret_cast<uint32_t*>(sB)[idx] = 0u;
   if (tid == 0) {
     tc::mbar_init(acc_bar, 1);
-    tc::mbar_init(h_bar, CS * (EPI_THREADS / 32));
+    tc::mbar_init(h_bar, 1);
     tc::fence_mbar_init();
   }
   if (warp == 8) tc::tmem_alloc(tmem_slot, 32);
@@ -339,8 +396,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
     const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
     const uint32_t ainc = (uint32_t)(2 * lboA) >> 4, binc = (uint32_t)(2 * LBO_B) >> 4;
     const int nkc = Kp / 16;
+    const uint32_t tx_bytes = (uint32_t)3 * H * NB * 2;      // all CTAs' (dpr, dpz, dgh_n) slices for 16 windows
+    if (n > 1 && tc::elect_one()) mbar_arrive_expect_tx(h_bar, tx_bytes);
+    __syncwarp();
     for (int it = 0; it < n - 1; ++it) {
-      mbar_wait_cluster(h_bar, it & 1);
+      tc::mbar_wait(h_bar, it & 1);
       fence_proxy_async_all();
       tc::tc_fence_after();
       const uint64_t bd0 = tc::make_smem_desc(tc::smem_u32(sB) + (uint32_t)((it & 1) * KC * LBO_B), LBO_B, SBO_B);
@@ -350,7 +410,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
         if (tc::elect_one()) tc::mma_f16_ss_lohi(tbase, alo, ahi, blo, bhi, idesc, kc > 0 ? 1u : 0u);
         alo += ainc; blo += binc;
       }
-      if (tc::elect_one()) tc::mma_commit(acc_bar);
+      if (tc::elect_one()) {
+        tc::mma_commit(acc_bar);
+        if (it + 1 < n - 1) mbar_arrive_expect_tx(h_bar, tx_bytes);
+      }
       __syncwarp();
     }
   } else {
@@ -363,8 +426,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
     float dhz[4] = {0.f, 0.f, 0.f, 0.f};
     const uint32_t woff = (uint32_t)(wq >> 1) * SBO_B + (uint32_t)(wq & 1) * 8;
     const uint32_t off0 = (uint32_t)(u >> 3) * LBO_B + (uint32_t)(u & 7) * 16 + woff;
-    const uint32_t off1 = (uint32_t)((H + u) >> 3) * LBO_B + (uint32_t)((H + u) & 7) * 16 + woff;
-    const uint32_t off2 = (uint32_t)((2 * H + u) >> 3) * LBO_B + (uint32_t)((2 * H + u) & 7) * 16 + woff;
+    const uint32_t off1 = (uint32_t)((Hp + u) >> 3) * LBO_B + (uint32_t)((Hp + u) & 7) * 16 + woff;
+    const uint32_t off2 = (uint32_t)((2 * Hp + u) >> 3) * LBO_B + (uint32_t)((2 * Hp + u) & 7) * 16 + woff;
     const uint32_t sB_addr = tc::smem_u32(sB), hbar_addr = tc::smem_u32(h_bar);
     const size_t gt_step = (size_t)4 * H * 16, gi_step = (size_t)G * 16, gn_step = (size_t)H * 16;
     const float* gt_p = valid ? P.gates + ((size_t)tile * n * 4 * H + u) * 16 + wb : nullptr;
@@ -375,11 +438,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
     // M = 64 accumulator: row i lives in TMEM lane 32*(i/16) + i%16  -> warp q drains rows 16q .. 16q+15
     const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
 
-    for (int t = n - 1; t >= 0; --t) {
-      const int it = n - 1 - t;
-      float dh[4], hp[4], r[4], z[4], nn[4], hn[4];
+    // everything of step `tt` that does not depend on the recurrence (software-pipelined one step ahead)
+    float dh[4], hp[4], r[4], z[4], nn[4], hn[4];
+    auto load_step = [&](int tt) {
       if (valid) {
-        const float4* gq = reinterpret_cast<const float4*>(gt_p + (size_t)t * gt_step);
+        const float4* gq = reinterpret_cast<const float4*>(gt_p + (size_t)tt * gt_step);
         float4 a = __ldg(gq), c = __ldg(gq + (size_t)H * 4), e = __ldg(gq + (size_t)2 * H * 4), f = __ldg(gq + (size_t)3 * H * 4);
         r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
         z[0] = c.x; z[1] = c.y; z[2] = c.z; z[3] = c.w;
@@ -389,10 +452,10 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
         for (int w = 0; w < 4; ++w) {
           float v = 0.f, p = 0.f;
           if (w < nvalid_w) {
-            size_t o = (row0 + (size_t)w * n + t) * H + u;
+            size_t o = (row0 + (size_t)w * n + tt) * H + u;
             if (P.dout) v = __ldg(P.dout + o);
-            if (it == 0 && P.dh_last) v += __ldg(P.dh_last + (size_t)(b0 + wb + w) * H + u);
-            if (t > 0) p = __ldg(P.out + o - H);
+            if (tt == n - 1 && P.dh_last) v += __ldg(P.dh_last + (size_t)(b0 + wb + w) * H + u);
+            if (tt > 0) p = __ldg(P.out + o - H);
           }
           dh[w] = v; hp[w] = p;
         }
@@ -400,6 +463,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
 #pragma unroll
         for (int w = 0; w < 4; ++w) { dh[w] = 0.f; hp[w] = 0.f; r[w] = 0.f; z[w] = 0.f; nn[w] = 0.f; hn[w] = 0.f; }
       }
+    };
+    load_step(n - 1);
+
+    for (int t = n - 1; t >= 0; --t) {
+      const int it = n - 1 - t;
       if (it > 0) {
         if (warp < 4) {
           tc::mbar_wait(acc_bar, (it - 1) & 1);
@@ -421,8 +489,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
           dh[2] += dhz[2] + acc.z * inv_scale; dh[3] += dhz[3] + acc.w * inv_scale;
         }
       }
+      float dpr[4], dpz[4], dpn[4], dgn[4];
       if (valid) {
-        float dpr[4], dpz[4], dpn[4], dgn[4];
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
           float d = dh[w];
@@ -434,30 +502,36 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
           dgn[w] = dpn[w] * r[w];
           dhz[w] = d * z[w];
         }
+      }
+      if (t > 0) {
+        uint32_t a0 = 0, a1 = 0, c0 = 0, c1 = 0, e0 = 0, e1 = 0;
+        if (valid) {
+          a0 = pack_h2(sat_h(dpr[0] * scale), sat_h(dpr[1] * scale)); a1 = pack_h2(sat_h(dpr[2] * scale), sat_h(dpr[3] * scale));
+          c0 = pack_h2(sat_h(dpz[0] * scale), sat_h(dpz[1] * scale)); c1 = pack_h2(sat_h(dpz[2] * scale), sat_h(dpz[3] * scale));
+          e0 = pack_h2(sat_h(dgn[0] * scale), sat_h(dgn[1] * scale)); e1 = pack_h2(sat_h(dgn[2] * scale), sat_h(dgn[3] * scale));
+        }
+        const uint32_t a2 = __shfl_xor_sync(0xffffffffu, a0, 1), a3 = __shfl_xor_sync(0xffffffffu, a1, 1);
+        const uint32_t c2 = __shfl_xor_sync(0xffffffffu, c0, 1), c3 = __shfl_xor_sync(0xffffffffu, c1, 1);
+        const uint32_t e2 = __shfl_xor_sync(0xffffffffu, e0, 1), e3 = __shfl_xor_sync(0xffffffffu, e1, 1);
+        if (valid && !(wq & 1)) {
+          const uint32_t buf = sB_addr + (uint32_t)((it & 1) * KC * LBO_B);
+          for (int rr = 0; rr < CS; ++rr) {
+            const uint32_t mb = mapa(hbar_addr, (uint32_t)rr);
+            st_async_v4(mapa(buf + off0, (uint32_t)rr), a0, a1, a2, a3, mb);
+            st_async_v4(mapa(buf + off1, (uint32_t)rr), c0, c1, c2, c3, mb);
+            st_async_v4(mapa(buf + off2, (uint32_t)rr), e0, e1, e2, e3, mb);
+          }
+        }
+      }
+      if (valid) {
+        // fp32 results for the weight-gradient GEMMs, after the hand-off
         float4* q4 = reinterpret_cast<float4*>(dgi_p + (size_t)t * gi_step);
         q4[0] = make_float4(dpr[0], dpr[1], dpr[2], dpr[3]);
         q4[(size_t)H * 4] = make_float4(dpz[0], dpz[1], dpz[2], dpz[3]);
         q4[(size_t)2 * H * 4] = make_float4(dpn[0], dpn[1], dpn[2], dpn[3]);
         *reinterpret_cast<float4*>(dgn_p + (size_t)t * gn_step) = make_float4(dgn[0], dgn[1], dgn[2], dgn[3]);
-        if (t > 0) {
-          const uint32_t buf = sB_addr + (uint32_t)((it & 1) * KC * LBO_B);
-          const uint32_t a0 = pack_h2(sat_h(dpr[0] * scale), sat_h(dpr[1] * scale)), a1 = pack_h2(sat_h(dpr[2] * scale), sat_h(dpr[3] * scale));
-          const uint32_t c0 = pack_h2(sat_h(dpz[0] * scale), sat_h(dpz[1] * scale)), c1 = pack_h2(sat_h(dpz[2] * scale), sat_h(dpz[3] * scale));
-          const uint32_t e0 = pack_h2(sat_h(dgn[0] * scale), sat_h(dgn[1] * scale)), e1 = pack_h2(sat_h(dgn[2] * scale), sat_h(dgn[3] * scale));
-          for (int rr = 0; rr < CS; ++rr) {
-            st_cluster_v2(mapa(buf + off0, (uint32_t)rr), a0, a1);
-            st_cluster_v2(mapa(buf + off1, (uint32_t)rr), c0, c1);
-            st_cluster_v2(mapa(buf + off2, (uint32_t)rr), e0, e1);
-          }
-        }
       }
-      if (it > 0) named_bar_sync(2, EPI_THREADS);
-      if (t > 0) {
-        fence_proxy_async_all();
-        __syncwarp();
-        if (lane == 0)
-          for (int rr = 0; rr < CS; ++rr) mbar_arrive_cluster(mapa(hbar_addr, (uint32_t)rr));
-      }
+      if (t > 0) load_step(t - 1);
     }
   }
   tc::tc_fence_before();
@@ -494,7 +568,10 @@ static int launch_cluster(Kern kern, const Params& P, int nblocks, int cs, size_
   return MTADGAT_OK;
 }
 
+static long long* g_dbg = nullptr;
 }  // namespace
+
+extern "C" void mtadgat_gru_debug_buffer(long long* dev_ptr) { g_dbg = dev_ptr; }
 
 int mtadgat_gru_cl_supported(int H, int Hs_rep) {
   ClGeom g;
@@ -510,6 +587,7 @@ int mtadgat_gru_cl_fwd_launch(const float* gi_t, const float* S, const float* hs
   ClFwdParams P;
   P.gi = gi_t; P.S = S; P.hsrc = hsrc; P.b_ih = b_ih; P.J = J; P.Hs = Hs; P.w_hh = w_hh; P.b_hh = b_hh;
   P.out = out; P.h_last = h_last; P.gates = gates_t; P.B = B; P.n = n; P.H = H; P.CS = g.CS; P.Uc = g.Uc;
+  P.dbg = g_dbg;
   return launch_cluster(gru_cl_fwd_kernel, P, cdiv(B, NB) * g.CS, g.CS, cl_fwd_smem(H, gi_t ? 0 : Hs), s);
 }
 

@@ -1,21 +1,23 @@
-// Tensor-core variant of the functor GEMM of gemm.cuh for sm_100a: tcgen05.mma kind::tf32, accumulators in TMEM.
+// Tensor-core variant of the functor GEMM of gemm.cuh for sm_100a: tcgen05.mma kind::f16 (bf16), accumulators in TMEM.
 //
 // The operands of the MTAD-GAT GEMMs are not TMA-friendly (row strides of 152 B, gathers over three tensors,
 // window-tiled layouts, on-the-fly masks), so the tile loaders stay functor-driven: 256 threads gather a
-// 128 x 16 (A) and BN x 16 (B) fp32 tile, split every value into two TF32 terms (hi = rna(x), lo = rna(x - hi))
-// and store them in the canonical K-major no-swizzle shared-memory layout; one thread then issues
-//   D += A_hi B_hi + A_lo B_hi + A_hi B_lo                (3xTF32: fp32-level accuracy, error ~2^-21)
+// 128 x 32 (A) and BN x 32 (B) fp32 tile, split every value into two bf16 terms (hi = rn(x), lo = rn(x - hi): 16
+// mantissa bits, fp32's exponent range, so gradients need no scaling) and store them in the canonical K-major
+// no-swizzle shared-memory layout; one thread then issues
+//   D += A_lo B_hi + A_hi B_lo + A_hi B_hi                (bf16x3: relative error ~2^-16 per product)
 // into a 128 x BN fp32 accumulator in TMEM.  Two shared-memory stages: the gather of k-tile i+1 overlaps the
 // asynchronous MMAs of k-tile i (stage reuse is gated by a tcgen05.commit mbarrier).  The epilogue pulls the
 // accumulator with tcgen05.ld (warp = 32 TMEM lanes = 32 rows) and hands every element to the store functor.
 #pragma once
+#include <cuda_bf16.h>
 #include "tc.cuh"
 
 extern int g_mtadgat_gemm_impl;   // 0 = SIMT fp32 (gemm.cuh), 1 = tensor cores (this file)
 
 namespace tcg {
 
-constexpr int BM = 128, BK = 16, NTHREADS = 256;
+constexpr int BM = 128, BK = 32, NTHREADS = 256;
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
   uint32_t u;
@@ -66,23 +68,27 @@ struct OpB {
   }
 };
 
-// split 8 fp32 values into TF32 hi / lo terms and store them as two 16-byte K groups of one operand row
-__device__ __forceinline__ void store_split8(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, uint32_t lbo, const float (&v)[8]) {
-  uint32_t h[8], l[8];
+// split 8 fp32 values into bf16 hi / lo terms and store each as ONE 16-byte K group of an operand row
+__device__ __forceinline__ void store_split8(uint8_t* hi_base, uint8_t* lo_base, uint32_t off, const float (&v)[8]) {
+  uint32_t h[4], l[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { h[j] = to_tf32(v[j]); l[j] = to_tf32(v[j] - __uint_as_float(h[j])); }
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    float2 hf = __bfloat1622float2(hh);
+    __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+    h[j] = *reinterpret_cast<uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<uint32_t*>(&ll);
+  }
   *reinterpret_cast<uint4*>(hi_base + off) = make_uint4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<uint4*>(hi_base + off + lbo) = make_uint4(h[4], h[5], h[6], h[7]);
   *reinterpret_cast<uint4*>(lo_base + off) = make_uint4(l[0], l[1], l[2], l[3]);
-  *reinterpret_cast<uint4*>(lo_base + off + lbo) = make_uint4(l[4], l[5], l[6], l[7]);
 }
 
 template <int BN>
 struct Smem {
-  static constexpr int LBO_A = BM * 16 + 16;          // bytes between 4-wide K groups (+16: bank spread)
+  static constexpr int LBO_A = BM * 16 + 16;          // bytes between 8-wide K groups (+16: bank spread)
   static constexpr int LBO_B = BN * 16 + 16;
-  static constexpr int A_BYTES = (BK / 4) * LBO_A;    // one of hi / lo
-  static constexpr int B_BYTES = (BK / 4) * LBO_B;
+  static constexpr int A_BYTES = (BK / 8) * LBO_A;    // one of hi / lo
+  static constexpr int B_BYTES = (BK / 8) * LBO_B;
   static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int TOTAL = 2 * STAGE + 64;
 };
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(int M, int N, int K, 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tbase = *slot;
-  const uint32_t idesc = make_idesc_tf32(BM, BN);
+  const uint32_t idesc = tc::make_idesc_f16(BM, BN, /*bf16=*/1);
   const int nkt = (kend - kbeg + BK - 1) / BK;
   // loader ownership: thread -> (line, 8-wide K half)
   const int a_row = tid & (BM - 1), a_kh = tid >> 7;
@@ -119,42 +125,56 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(int M, int N, int K, 
   const bool b_ok = b_active && (n0 + b_row < N);
   const typename OpB<BL>::Ctx bctx = OpB<BL>::line(Bm, z, b_ok ? n0 + b_row : 0);
 
+  // software pipeline: the global loads of k-tile kt+1 are issued right after the MMAs of k-tile kt, so their
+  // latency overlaps the tensor-core work and the stage hand-off instead of sitting in front of every store
+  float va0[8], va1[8], vb0[8], vb1[8];          // thread owns 16 consecutive K of its A line and of its B line
+  auto load_tile = [&](int kt) {
+    const int k0 = kbeg + kt * BK;
+    if (a_ok) {
+      OpA<AL>::load8(A, actx, z, k0 + 16 * a_kh, kend, va0);
+      OpA<AL>::load8(A, actx, z, k0 + 16 * a_kh + 8, kend, va1);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { va0[j] = 0.f; va1[j] = 0.f; }
+    }
+    if (b_ok) {
+      OpB<BL>::load8(Bm, bctx, z, k0 + 16 * b_kh, kend, vb0);
+      OpB<BL>::load8(Bm, bctx, z, k0 + 16 * b_kh + 8, kend, vb1);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { vb0[j] = 0.f; vb1[j] = 0.f; }
+    }
+  };
+  if (nkt > 0) load_tile(0);
+
   for (int kt = 0; kt < nkt; ++kt) {
     const int s = kt & 1;
     uint8_t* sAh = smem_raw + s * S::STAGE;
     uint8_t* sAl = sAh + S::A_BYTES;
     uint8_t* sBh = sAl + S::A_BYTES;
     uint8_t* sBl = sBh + S::B_BYTES;
-    const int k0 = kbeg + kt * BK;
-    // issue the global loads first, then wait for the stage to drain
-    float va[8], vb[8];
-    if (a_ok) OpA<AL>::load8(A, actx, z, k0 + 8 * a_kh, kend, va);
-    else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) va[j] = 0.f;
-    }
-    if (b_ok) OpB<BL>::load8(Bm, bctx, z, k0 + 8 * b_kh, kend, vb);
-    else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) vb[j] = 0.f;
-    }
     if (kt >= 2) tc::mbar_wait(bars + s, ((kt >> 1) - 1) & 1);     // MMAs that read this stage are done
-    store_split8(sAh, sAl, (uint32_t)(2 * a_kh) * S::LBO_A + (uint32_t)a_row * 16, S::LBO_A, va);
-    if (b_active) store_split8(sBh, sBl, (uint32_t)(2 * b_kh) * S::LBO_B + (uint32_t)b_row * 16, S::LBO_B, vb);
+    store_split8(sAh, sAl, (uint32_t)(2 * a_kh) * S::LBO_A + (uint32_t)a_row * 16, va0);
+    store_split8(sAh, sAl, (uint32_t)(2 * a_kh + 1) * S::LBO_A + (uint32_t)a_row * 16, va1);
+    if (b_active) {
+      store_split8(sBh, sBl, (uint32_t)(2 * b_kh) * S::LBO_B + (uint32_t)b_row * 16, vb0);
+      store_split8(sBh, sBl, (uint32_t)(2 * b_kh + 1) * S::LBO_B + (uint32_t)b_row * 16, vb1);
+    }
+    if (kt + 1 < nkt) load_tile(kt + 1);
     tc::fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
       tc::tc_fence_after();
       const uint32_t ah = tc::smem_u32(sAh), al = tc::smem_u32(sAl), bh = tc::smem_u32(sBh), bl = tc::smem_u32(sBl);
 #pragma unroll
-      for (int j = 0; j < BK / 8; ++j) {
+      for (int j = 0; j < BK / 16; ++j) {
         uint64_t dAh = tc::make_smem_desc(ah + (uint32_t)(2 * j) * S::LBO_A, S::LBO_A, 128);
         uint64_t dAl = tc::make_smem_desc(al + (uint32_t)(2 * j) * S::LBO_A, S::LBO_A, 128);
         uint64_t dBh = tc::make_smem_desc(bh + (uint32_t)(2 * j) * S::LBO_B, S::LBO_B, 128);
         uint64_t dBl = tc::make_smem_desc(bl + (uint32_t)(2 * j) * S::LBO_B, S::LBO_B, 128);
-        mma_tf32_ss(tbase, dAl, dBh, idesc, (kt > 0 || j > 0) ? 1u : 0u);   // small terms first
-        mma_tf32_ss(tbase, dAh, dBl, idesc, 1u);
-        mma_tf32_ss(tbase, dAh, dBh, idesc, 1u);
+        tc::mma_f16_ss(tbase, dAl, dBh, idesc, (kt > 0 || j > 0) ? 1u : 0u);   // small terms first
+        tc::mma_f16_ss(tbase, dAh, dBl, idesc, 1u);
+        tc::mma_f16_ss(tbase, dAh, dBh, idesc, 1u);
       }
       tc::mma_commit(bars + s);
       if (kt == nkt - 1) tc::mma_commit(bars + 2);

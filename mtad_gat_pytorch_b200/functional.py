@@ -257,7 +257,7 @@ def set_gru_impl(name):
 
 
 def set_gemm_impl(name):
-    """'tc' (default): tcgen05 3xTF32 GEMMs; 'fp32': SIMT fp32 GEMMs."""
+    """'tc' (default): tcgen05 bf16x3 GEMMs; 'fp32': SIMT fp32 GEMMs."""
     check(lib.mtadgat_set_gemm_impl({"fp32": 0, "tc": 1}[name]))
 
 
