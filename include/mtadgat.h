@@ -15,6 +15,10 @@
  *   - dropout: multipliers are a pure function of (*seed, rng stream id, element index) (Philox4x32-10), so
  *     forward and backward regenerate the same mask; `seed` points to a device uint64 (CUDA-graph safe)
  *   - gradients of parameters are overwritten (not accumulated); data gradients honour `*_accumulate`
+ *   - `parts` of a *_bwd: bit 0 = recurrence / data-gradient work (the critical path of backpropagation),
+ *     bit 1 = parameter-gradient work (reads what bit 0 left in `scratch`).  3 = everything on `stream`;
+ *     the host layer issues 1 on the main stream and 2 on a side stream so parameter gradients overlap the
+ *     upstream layers' backward.
  */
 #ifndef MTADGAT_H_
 #define MTADGAT_H_
@@ -50,7 +54,7 @@ int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* lin_b, cons
                     const float* gout, const float* saved, float* scratch, float* dx, int dx_accumulate,
                     float* dlin_w, float* dlin_b, float* da, float* dbias /*nullable*/, int B, int n, int k, int E,
                     int feature, int use_gatv2, float alpha, float p_drop, const unsigned long long* seed,
-                    void* stream);
+                    int parts, void* stream);
 
 /* ---- GRULayer.forward modules.py:235-238 (one nn.GRU layer, batch_first, h0=0, gate order r,z,n).
  *      The input is given as up to three column slices x0|x1|x2 of widths k0,k1,k2 (the torch.cat of
@@ -65,7 +69,7 @@ int mtadgat_gru_bwd(const float* x0, const float* x1, const float* x2, int k0, i
                     const float* w_hh, const float* out, const float* saved, const float* dout /*nullable*/,
                     const float* dh_last /*nullable*/, float* scratch, float* dx0, float* dx1, float* dx2, int acc0,
                     int acc1, int acc2, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int B, int n, int H,
-                    void* stream);
+                    int parts, void* stream);
 
 /* ---- ReconstructionModel.forward modules.py:276-281: decoder GRU over the reference's scrambled repeat
  *      rep[b,t,c] = h_src[b,(t*Hs+c)//n] (modules.py:279), all n outputs (B,n,R). ---- */
@@ -78,7 +82,7 @@ int mtadgat_gru_rep_fwd(const float* h_src, const float* w_ih, const float* w_hh
 int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const float* w_hh, const float* out,
                         const float* saved, const float* dout, float* scratch, float* dh_src, int dh_accumulate,
                         float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int B, int n, int Hs, int R,
-                        void* stream);
+                        int parts, void* stream);
 
 /* ---- nn.Linear (+ReLU, +Dropout): Forecasting_Model.forward modules.py:307-311, recon fc modules.py:282.
  *      x (M,I), w (O,I), b (O), y (M,O); act 0 none / 1 relu. ---- */
@@ -87,7 +91,7 @@ int mtadgat_linear_fwd(const float* x, const float* w, const float* b, float* y,
 int mtadgat_linear_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx /*nullable*/,
                        int dx_accumulate, float* dw, float* db, float* scratch /* M*O floats; nullable if act=0,p=0 */,
                        int M, int I, int O, int act, float p_drop, const unsigned long long* seed,
-                       unsigned int rng_stream, void* stream);
+                       unsigned int rng_stream, int parts, void* stream);
 
 /* ---- recurrence implementation: 1 (default) = persistent tcgen05/TMEM kernel, fp16 operands with fp32
  *      accumulation and fp32 hidden state (hidden sizes 8..256); 0 = fp32 SIMT kernel.  mtadgat_tc_probe runs one

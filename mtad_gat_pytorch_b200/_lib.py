@@ -26,20 +26,20 @@ SIGNATURES = {
     "mtadgat_gat_saved_floats": (_LL, [_I, _I, _I, _I, _I, _I, _I]),
     "mtadgat_gat_bwd_scratch_floats": (_LL, [_I, _I, _I, _I, _I, _I]),
     "mtadgat_gat_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _P, _P]),
-    "mtadgat_gat_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _P, _P]),
+    "mtadgat_gat_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _P, _I, _P]),
     "mtadgat_gru_saved_floats": (_LL, [_I, _I, _I, _I]),
     "mtadgat_gru_fwd_scratch_floats": (_LL, [_I, _I, _I]),
     "mtadgat_gru_bwd_scratch_floats": (_LL, [_I, _I, _I]),
     "mtadgat_gru_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mtadgat_gru_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I,
-                             _P, _P, _P, _P, _I, _I, _I, _P]),
+                             _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mtadgat_rep_J": (_I, [_I, _I]),
     "mtadgat_gru_rep_saved_floats": (_LL, [_I, _I, _I, _I, _I]),
     "mtadgat_gru_rep_bwd_scratch_floats": (_LL, [_I, _I, _I, _I]),
     "mtadgat_gru_rep_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "mtadgat_gru_rep_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mtadgat_gru_rep_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mtadgat_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _U, _P]),
-    "mtadgat_linear_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _P, _U, _P]),
+    "mtadgat_linear_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _P, _U, _I, _P]),
     "mtadgat_set_gemm_impl": (_I, [_I]),
     "mtadgat_get_gemm_impl": (_I, []),
     "mtadgat_set_gru_impl": (_I, [_I]),

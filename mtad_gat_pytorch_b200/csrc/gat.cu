@@ -688,9 +688,10 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
                                const float* out, const float* gout, const float* saved, float* scratch, float* dx,
                                int dx_accumulate, float* dlin_w, float* dlin_b, float* da, float* dbias, int B, int n,
                                int k, int E, int feature, int use_gatv2, float alpha, float p_drop,
-                               const unsigned long long* seed, void* stream) {
+                               const unsigned long long* seed, int parts, void* stream) {
   MG_CHECK_ARG(x && lin_w && lin_b && a && out && gout && saved && scratch && dx && dlin_w && dlin_b && da,
                "gat_bwd: null pointer");
+  MG_CHECK_ARG(parts >= 1 && parts <= 3, "gat_bwd: parts must be 1 (data), 2 (parameters) or 3 (both)");
   cudaStream_t s = (cudaStream_t)stream;
   GatDims d = make_dims(B, n, k, E, feature, use_gatv2);
   SavedLayout L = saved_layout(d, E, 1);
@@ -703,8 +704,9 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
   float* dbp = dwp + (size_t)d.D * d.NC;
   const float inv_keep = 1.f / (1.f - p_drop);
   const uint32_t strm = feature ? 1u : 2u;
+  const bool do_data = parts & 1, do_par = parts & 2;
   // ---- bwd1 ----
-  {
+  if (do_data) {
     int RB = min(d.K, 64), JT = min(d.K, 64);
     size_t smem;
     for (;;) {
@@ -723,12 +725,12 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
     MG_COUNT_LAUNCH();
   }
   // ---- dbias ----
-  if (dbias) {
+  if (dbias && do_par) {
     MG_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * (size_t)d.K * d.K, s));
     launch_colsum(B, d.K * d.K, DeCols{de, d.K, d.Kp}, dbias, s);
   }
   // ---- bwd2 (two passes) ----
-  {
+  if (do_data) {
     int DT = d.E > 0 ? d.E : 1;
     size_t smem;
     for (;;) {
@@ -750,22 +752,22 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
     }
   }
   // ---- weight-side GEMMs ----
-  MG_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * ((size_t)d.D * d.NC + d.NC), s));
-  {
+  if (do_par) MG_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * ((size_t)d.D * d.NC + d.NC), s));
+  if (do_par) {
     DpqB Bq{dpqt, d.NC, d.Kp, d.K};
     StAtomic2 C{dwp, d.NC};
     if (feature) launch_gemm_splitk(d.D, d.NC, B * d.K, NodeAT<true>{x, n, k, d.K}, Bq, C, s);
     else launch_gemm_splitk(d.D, d.NC, B * d.K, NodeAT<false>{x, n, k, d.K}, Bq, C, s);
     launch_colsum(B * d.K, d.NC, DpqCols{dpqt, d.NC, d.Kp, d.K}, dbp, s);
   }
-  {
+  if (do_par) {
     int nw = 8;
     gat_prep_bwd_kernel<<<cdiv(E, nw), nw * 32, 0, s>>>(lin_w, lin_b, a, meta, alpha, d.D, E, use_gatv2, dwp, dbp,
                                                         dlin_w, dlin_b, da);
     MG_COUNT_LAUNCH();
   }
   // ---- data gradient: dV = A~^T dS + dPQ Wp^T ----
-  {
+  if (do_data) {
     AttTA A{att, d.K, d.Kp, p_drop, inv_keep, seed, strm};
     DsB Bd{ds, d.K, d.D};
     if (feature) launch_gemm_batched(B, d.K, d.D, d.K, A, Bd, StNodeAcc<true>{dx, n, k, dx_accumulate}, s);

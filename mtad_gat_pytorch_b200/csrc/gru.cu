@@ -574,26 +574,31 @@ extern "C" int mtadgat_gru_bwd(const float* x0, const float* x1, const float* x2
                                const float* w_ih, const float* w_hh, const float* out, const float* saved,
                                const float* dout, const float* dh_last, float* scratch, float* dx0, float* dx1,
                                float* dx2, int acc0, int acc1, int acc2, float* dw_ih, float* dw_hh, float* db_ih,
-                               float* db_hh, int B, int n, int H, void* stream) {
+                               float* db_hh, int B, int n, int H, int parts, void* stream) {
   MG_CHECK_ARG(x0 && w_ih && w_hh && out && saved && scratch && dw_ih && dw_hh && db_ih && db_hh, "gru_bwd: null pointer");
   MG_CHECK_ARG(dout || dh_last, "gru_bwd: need dout and/or dh_last");
+  MG_CHECK_ARG(parts >= 1 && parts <= 3, "gru_bwd: parts must be 1 (recurrence + data), 2 (parameters) or 3");
   cudaStream_t s = (cudaStream_t)stream;
   const int I = k0 + k1 + k2, G = 3 * H, Bp = tiled_B(B), Rt = Bp * n;
   const float* gates = saved + al4((size_t)3 * H * H);
   float* dgi = scratch; float* dghn = scratch + (size_t)Rt * G;
   unsigned int* gmax = reinterpret_cast<unsigned int*>(scratch + (size_t)Rt * 4 * H);
-  int rc = run_recurrence_bwd(gates, out, w_hh, dout, dh_last, gmax, dgi, dghn, B, n, H, s);
-  if (rc) return rc;
-  MG_CUDA(cudaMemsetAsync(dw_ih, 0, sizeof(float) * (size_t)G * I, s));
-  MG_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * (size_t)G * H, s));
-  MG_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)G, s));
-  MG_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)G, s));
-  launch_gemm_splitk(G, I, Rt, TiledT{dgi, G}, Cat3BT{x0, x1, x2, k0, k1, k2, n, B}, StAtomic2{dw_ih, I}, s);
-  launch_gemm_splitk(G, H, Rt, DghTT{dgi, dghn, H}, HprevBT{out, n, H, B}, StAtomic2{dw_hh, H}, s);
-  launch_colsum_tiled(dgi, Rt / 16, G, db_ih, s);
-  launch_colsum_tiled(dghn, Rt / 16, H, db_hh + 2 * H, s);
-  MG_CUDA(cudaMemcpyAsync(db_hh, db_ih, sizeof(float) * (size_t)2 * H, cudaMemcpyDeviceToDevice, s));
-  if (dx0 || dx1 || dx2) {
+  if (parts & 1) {
+    int rc = run_recurrence_bwd(gates, out, w_hh, dout, dh_last, gmax, dgi, dghn, B, n, H, s);
+    if (rc) return rc;
+  }
+  if (parts & 2) {
+    MG_CUDA(cudaMemsetAsync(dw_ih, 0, sizeof(float) * (size_t)G * I, s));
+    MG_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * (size_t)G * H, s));
+    MG_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)G, s));
+    MG_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)G, s));
+    launch_gemm_splitk(G, I, Rt, TiledT{dgi, G}, Cat3BT{x0, x1, x2, k0, k1, k2, n, B}, StAtomic2{dw_ih, I}, s);
+    launch_gemm_splitk(G, H, Rt, DghTT{dgi, dghn, H}, HprevBT{out, n, H, B}, StAtomic2{dw_hh, H}, s);
+    launch_colsum_tiled(dgi, Rt / 16, G, db_ih, s);
+    launch_colsum_tiled(dghn, Rt / 16, H, db_hh + 2 * H, s);
+    MG_CUDA(cudaMemcpyAsync(db_hh, db_ih, sizeof(float) * (size_t)2 * H, cudaMemcpyDeviceToDevice, s));
+  }
+  if ((parts & 1) && (dx0 || dx1 || dx2)) {
     // dx = dgi W_ih : A(m=r,kk=g) = dgi_t[r][g] ; B(kk=g, n=i) = w_ih[g, i]
     launch_gemm_batched(1, Rt, I, G, TiledA{dgi, G}, Strided2<true>{w_ih, 0, I, 1},
                         StCat3T{dx0, dx1, dx2, k0, k1, k2, n, B, acc0, acc1, acc2}, s);
@@ -635,7 +640,7 @@ extern "C" int mtadgat_gru_rep_fwd(const float* h_src, const float* w_ih, const 
 extern "C" int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const float* w_hh, const float* out,
                                    const float* saved, const float* dout, float* scratch, float* dh_src,
                                    int dh_accumulate, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int B,
-                                   int n, int Hs, int R, void* stream) {
+                                   int n, int Hs, int R, int parts, void* stream) {
   MG_CHECK_ARG(h_src && w_ih && w_hh && out && saved && dout && scratch && dh_src && dw_ih && dw_hh && db_ih && db_hh,
                "gru_rep_bwd: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
@@ -644,21 +649,26 @@ extern "C" int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const 
   const float* gates = S + al4((size_t)n * J * G);
   float* dgi = scratch; float* dghn = dgi + (size_t)Rt * G; float* dS = dghn + (size_t)Rt * R;
   unsigned int* gmax = reinterpret_cast<unsigned int*>(dS + (size_t)n * J * G);
-  int rc = run_recurrence_bwd(gates, out, w_hh, dout, nullptr, gmax, dgi, dghn, B, n, R, s);
-  if (rc) return rc;
-  MG_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * (size_t)G * R, s));
-  MG_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)G, s));
-  MG_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)G, s));
-  launch_gemm_splitk(G, R, Rt, DghTT{dgi, dghn, R}, HprevBT{out, n, R, B}, StAtomic2{dw_hh, R}, s);
-  launch_colsum_tiled(dgi, Rt / 16, G, db_ih, s);
-  launch_colsum_tiled(dghn, Rt / 16, R, db_hh + 2 * R, s);
-  MG_CUDA(cudaMemcpyAsync(db_hh, db_ih, sizeof(float) * (size_t)2 * R, cudaMemcpyDeviceToDevice, s));
-  rep_dS_kernel<<<cdiv((long long)n * J * G, 256), 256, 0, s>>>(dgi, h_src, B, n, Hs, G, J, dS);
-  MG_COUNT_LAUNCH();
-  rep_dw_kernel<<<cdiv((long long)G * Hs, 256), 256, 0, s>>>(dS, n, Hs, G, J, dw_ih);
-  MG_COUNT_LAUNCH();
-  rep_dh_kernel<<<cdiv((long long)(Bp / 16) * Hs, 8), 256, 0, s>>>(dgi, S, B, n, Hs, G, J, dh_src, dh_accumulate);
-  MG_COUNT_LAUNCH();
+  MG_CHECK_ARG(parts >= 1 && parts <= 3, "gru_rep_bwd: parts must be 1 (recurrence + data), 2 (parameters) or 3");
+  if (parts & 1) {
+    int rc = run_recurrence_bwd(gates, out, w_hh, dout, nullptr, gmax, dgi, dghn, B, n, R, s);
+    if (rc) return rc;
+    rep_dh_kernel<<<cdiv((long long)(Bp / 16) * Hs, 8), 256, 0, s>>>(dgi, S, B, n, Hs, G, J, dh_src, dh_accumulate);
+    MG_COUNT_LAUNCH();
+  }
+  if (parts & 2) {
+    MG_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * (size_t)G * R, s));
+    MG_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)G, s));
+    MG_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)G, s));
+    launch_gemm_splitk(G, R, Rt, DghTT{dgi, dghn, R}, HprevBT{out, n, R, B}, StAtomic2{dw_hh, R}, s);
+    launch_colsum_tiled(dgi, Rt / 16, G, db_ih, s);
+    launch_colsum_tiled(dghn, Rt / 16, R, db_hh + 2 * R, s);
+    MG_CUDA(cudaMemcpyAsync(db_hh, db_ih, sizeof(float) * (size_t)2 * R, cudaMemcpyDeviceToDevice, s));
+    rep_dS_kernel<<<cdiv((long long)n * J * G, 256), 256, 0, s>>>(dgi, h_src, B, n, Hs, G, J, dS);
+    MG_COUNT_LAUNCH();
+    rep_dw_kernel<<<cdiv((long long)G * Hs, 256), 256, 0, s>>>(dS, n, Hs, G, J, dw_ih);
+    MG_COUNT_LAUNCH();
+  }
   MG_CHECK_LAUNCH("gru_rep_bwd");
   return MTADGAT_OK;
 }

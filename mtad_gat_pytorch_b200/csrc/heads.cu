@@ -47,28 +47,34 @@ extern "C" int mtadgat_linear_fwd(const float* x, const float* w, const float* b
 
 extern "C" int mtadgat_linear_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx,
                                   int dx_accumulate, float* dw, float* db, float* scratch, int M, int I, int O, int act,
-                                  float p_drop, const unsigned long long* seed, unsigned int rng_stream, void* stream) {
+                                  float p_drop, const unsigned long long* seed, unsigned int rng_stream, int parts,
+                                  void* stream) {
   MG_CHECK_ARG(x && w && y && dy && dw && db, "linear_bwd: null pointer");
+  MG_CHECK_ARG(parts >= 1 && parts <= 3, "linear_bwd: parts must be 1 (data), 2 (parameters) or 3 (both)");
   cudaStream_t s = (cudaStream_t)stream;
   const float* src = dy;
   if (act != ACT_NONE || p_drop > 0.f) {
     MG_CHECK_ARG(scratch, "linear_bwd: scratch (M*O floats) required when an activation or dropout is fused");
     long long numel = (long long)M * O;
-    dpre_kernel<<<cdiv(numel, 256), 256, 0, s>>>(dy, y, scratch, numel, act, p_drop, 1.f / (1.f - p_drop), seed, rng_stream);
-    MG_COUNT_LAUNCH();
+    if (parts & 1) {
+      dpre_kernel<<<cdiv(numel, 256), 256, 0, s>>>(dy, y, scratch, numel, act, p_drop, 1.f / (1.f - p_drop), seed, rng_stream);
+      MG_COUNT_LAUNCH();
+    }
     src = scratch;
   }
-  if (dx) {
+  if (dx && (parts & 1)) {
     // dx = dpre W : A(m,kk=o) = dpre[m*O+o] ; B(kk=o, n=i) = w[o*I + i]
     launch_gemm_batched(1, M, I, O, Strided2<true>{src, 0, O, 1}, Strided2<true>{w, 0, I, 1},
                         StStrided{dx, 0, I, 1, nullptr, ACT_NONE, dx_accumulate}, s);
   }
-  MG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)O * I, s));
-  MG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)O, s));
-  // dw[o][i] = sum_m dpre[m][o] x[m][i] : A(m=o, kk=row) = dpre[row*O + o]
-  launch_gemm_splitk(O, I, M, Strided2<false>{src, 0, 1, O}, Strided2<true>{x, 0, I, 1},
-                     StStrided{dw, 0, I, 1, nullptr, ACT_NONE, 0}, s);
-  launch_colsum(M, O, Strided2<true>{src, 0, O, 1}, db, s);
+  if (parts & 2) {
+    MG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)O * I, s));
+    MG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)O, s));
+    // dw[o][i] = sum_m dpre[m][o] x[m][i] : A(m=o, kk=row) = dpre[row*O + o]
+    launch_gemm_splitk(O, I, M, Strided2<false>{src, 0, 1, O}, Strided2<true>{x, 0, I, 1},
+                       StStrided{dw, 0, I, 1, nullptr, ACT_NONE, 0}, s);
+    launch_colsum(M, O, Strided2<true>{src, 0, O, 1}, db, s);
+  }
   MG_CHECK_LAUNCH("linear_bwd");
   return MTADGAT_OK;
 }

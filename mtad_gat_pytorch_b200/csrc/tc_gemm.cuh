@@ -160,25 +160,33 @@ __global__ void __launch_bounds__(NTHREADS) tc_gemm_kernel(int M, int N, int K, 
       store_split8(sBh, sBl, (uint32_t)(2 * b_kh) * S::LBO_B + (uint32_t)b_row * 16, vb0);
       store_split8(sBh, sBl, (uint32_t)(2 * b_kh + 1) * S::LBO_B + (uint32_t)b_row * 16, vb1);
     }
-    if (kt + 1 < nkt) load_tile(kt + 1);
     tc::fence_proxy_async_smem();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
+      // whole warp runs the (uniform) descriptor arithmetic, one elected lane issues
       tc::tc_fence_after();
-      const uint32_t ah = tc::smem_u32(sAh), al = tc::smem_u32(sAl), bh = tc::smem_u32(sBh), bl = tc::smem_u32(sBl);
+      const uint32_t sbase = tc::smem_u32(smem_raw) + (uint32_t)(s * S::STAGE);
 #pragma unroll
       for (int j = 0; j < BK / 16; ++j) {
-        uint64_t dAh = tc::make_smem_desc(ah + (uint32_t)(2 * j) * S::LBO_A, S::LBO_A, 128);
-        uint64_t dAl = tc::make_smem_desc(al + (uint32_t)(2 * j) * S::LBO_A, S::LBO_A, 128);
-        uint64_t dBh = tc::make_smem_desc(bh + (uint32_t)(2 * j) * S::LBO_B, S::LBO_B, 128);
-        uint64_t dBl = tc::make_smem_desc(bl + (uint32_t)(2 * j) * S::LBO_B, S::LBO_B, 128);
-        tc::mma_f16_ss(tbase, dAl, dBh, idesc, (kt > 0 || j > 0) ? 1u : 0u);   // small terms first
-        tc::mma_f16_ss(tbase, dAh, dBl, idesc, 1u);
-        tc::mma_f16_ss(tbase, dAh, dBh, idesc, 1u);
+        const uint32_t ao = (uint32_t)(2 * j) * S::LBO_A, bo = (uint32_t)(2 * j) * S::LBO_B;
+        const uint64_t dAh = tc::make_smem_desc(sbase + ao, S::LBO_A, 128);
+        const uint64_t dAl = tc::make_smem_desc(sbase + S::A_BYTES + ao, S::LBO_A, 128);
+        const uint64_t dBh = tc::make_smem_desc(sbase + 2 * S::A_BYTES + bo, S::LBO_B, 128);
+        const uint64_t dBl = tc::make_smem_desc(sbase + 2 * S::A_BYTES + S::B_BYTES + bo, S::LBO_B, 128);
+        if (tc::elect_one()) {
+          tc::mma_f16_ss(tbase, dAl, dBh, idesc, (kt > 0 || j > 0) ? 1u : 0u);   // small terms first
+          tc::mma_f16_ss(tbase, dAh, dBl, idesc, 1u);
+          tc::mma_f16_ss(tbase, dAh, dBh, idesc, 1u);
+        }
       }
-      tc::mma_commit(bars + s);
-      if (kt == nkt - 1) tc::mma_commit(bars + 2);
+      if (tc::elect_one()) {
+        tc::mma_commit(bars + s);
+        if (kt == nkt - 1) tc::mma_commit(bars + 2);
+      }
+      __syncwarp();
     }
+    // prefetch AFTER the proxy fence (the fence waits for this thread's outstanding memory operations)
+    if (kt + 1 < nkt) load_tile(kt + 1);
   }
   // ---- epilogue: warp w reads TMEM lanes 32*(w&3).., columns [ (w>>2)*BN/2, +BN/2 ) ----
   if (nkt > 0) {

@@ -70,6 +70,44 @@ def dropout_multipliers(numel, p, seed_t, rng_stream):
 
 
 # ---------------------------------------------------------------------------------------------------
+# parameter gradients on a side stream: every *_bwd entry point splits into `parts=1` (recurrence / data gradients: the
+# critical path of backpropagation, stays on the current stream) and `parts=2` (parameter gradients), which is
+# issued on a per-device side stream and joined once, when the autograd engine finishes the backward pass.
+# ---------------------------------------------------------------------------------------------------
+PARAM_SIDE_STREAM = True
+_param_streams = {}
+_join_pending = set()
+
+
+def _param_stream(device):
+    s = _param_streams.get(device)
+    if s is None:
+        s = _param_streams[device] = torch.cuda.Stream(device=device)
+    return s
+
+
+def _run_bwd(device, call, tensors):
+    """call(parts, stream_ptr): issue the data part here, the parameter part on the side stream."""
+    if not PARAM_SIDE_STREAM:
+        call(3, _stream())
+        return
+    cur = torch.cuda.current_stream(device)
+    call(1, cur.cuda_stream)
+    ps = _param_stream(device)
+    ps.wait_stream(cur)
+    call(2, ps.cuda_stream)
+    for t in tensors:
+        if t is not None and t.numel() > 0:
+            t.record_stream(ps)
+    if device not in _join_pending:
+        _join_pending.add(device)
+
+        def _join():
+            _join_pending.discard(device)
+            torch.cuda.current_stream(device).wait_stream(ps)
+        torch.autograd.Variable._execution_engine.queue_callback(_join)
+
+
 class ConvReluFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b):
@@ -124,10 +162,11 @@ class GatFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         dw, db, da = torch.empty_like(lin_w), torch.empty_like(lin_b), torch.empty_like(a)
         dbias = torch.empty(K, K, dtype=torch.float32, device=x.device) if has_bias else None
-        check(lib.mtadgat_gat_bwd(x.data_ptr(), lin_w.data_ptr(), lin_b.data_ptr(), a.data_ptr(), out.data_ptr(),
-                                  gout.data_ptr(), saved.data_ptr(), scratch.data_ptr(), dx.data_ptr(), 0,
-                                  dw.data_ptr(), db.data_ptr(), da.data_ptr(), _ptr(dbias), B, n, k, E, feature, v2,
-                                  alpha, p, seed_t.data_ptr() if has_seed else None, _stream()))
+        _run_bwd(x.device, lambda parts, st: check(lib.mtadgat_gat_bwd(
+            x.data_ptr(), lin_w.data_ptr(), lin_b.data_ptr(), a.data_ptr(), out.data_ptr(), gout.data_ptr(),
+            saved.data_ptr(), scratch.data_ptr(), dx.data_ptr(), 0, dw.data_ptr(), db.data_ptr(), da.data_ptr(),
+            _ptr(dbias), B, n, k, E, feature, v2, alpha, p, seed_t.data_ptr() if has_seed else None, parts, st)),
+            (x, lin_w, lin_b, a, saved, scratch, dw, db, da, dbias))
         return dx, dw, db, da, dbias, None, None, None, None, None
 
 
@@ -172,11 +211,11 @@ class GruFn(torch.autograd.Function):
         dw_ih, dw_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
         db_ih = torch.empty(3 * H, dtype=torch.float32, device=out.device)
         db_hh = torch.empty_like(db_ih)
-        check(lib.mtadgat_gru_bwd(_ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), ks[0], ks[1], ks[2], w_ih.data_ptr(),
-                                  w_hh.data_ptr(), out.data_ptr(), saved.data_ptr(), _ptr(dout), _ptr(dh_last),
-                                  scratch.data_ptr(), _ptr(dxs[0]), _ptr(dxs[1]), _ptr(dxs[2]), 0, 0, 0,
-                                  dw_ih.data_ptr(), dw_hh.data_ptr(), db_ih.data_ptr(), db_hh.data_ptr(), B, n, H,
-                                  _stream()))
+        _run_bwd(out.device, lambda parts, st: check(lib.mtadgat_gru_bwd(
+            _ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), ks[0], ks[1], ks[2], w_ih.data_ptr(), w_hh.data_ptr(), out.data_ptr(),
+            saved.data_ptr(), _ptr(dout), _ptr(dh_last), scratch.data_ptr(), _ptr(dxs[0]), _ptr(dxs[1]), _ptr(dxs[2]),
+            0, 0, 0, dw_ih.data_ptr(), dw_hh.data_ptr(), db_ih.data_ptr(), db_hh.data_ptr(), B, n, H, parts, st)),
+            (xs[0], xs[1], xs[2], out, scratch, dw_ih, dw_hh, db_ih, db_hh))
         return dxs[0], dxs[1], dxs[2], dw_ih, dw_hh, db_ih, db_hh, None
 
 
@@ -210,10 +249,11 @@ class GruRepFn(torch.autograd.Function):
         dw_ih, dw_hh = torch.empty_like(w_ih), torch.empty_like(w_hh)
         db_ih = torch.empty(3 * R, dtype=torch.float32, device=out.device)
         db_hh = torch.empty_like(db_ih)
-        check(lib.mtadgat_gru_rep_bwd(h_src.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), out.data_ptr(),
-                                      saved.data_ptr(), dout.data_ptr(), scratch.data_ptr(), dh.data_ptr(), 0,
-                                      dw_ih.data_ptr(), dw_hh.data_ptr(), db_ih.data_ptr(), db_hh.data_ptr(), B, n,
-                                      Hs, R, _stream()))
+        _run_bwd(out.device, lambda parts, st: check(lib.mtadgat_gru_rep_bwd(
+            h_src.data_ptr(), w_ih.data_ptr(), w_hh.data_ptr(), out.data_ptr(), saved.data_ptr(), dout.data_ptr(),
+            scratch.data_ptr(), dh.data_ptr(), 0, dw_ih.data_ptr(), dw_hh.data_ptr(), db_ih.data_ptr(),
+            db_hh.data_ptr(), B, n, Hs, R, parts, st)),
+            (h_src, out, saved, scratch, dw_ih, dw_hh, db_ih, db_hh))
         return dh, dw_ih, dw_hh, db_ih, db_hh, None
 
 
@@ -244,9 +284,10 @@ class LinearFn(torch.autograd.Function):
         dw = torch.empty_like(w)
         db = torch.empty(O, dtype=torch.float32, device=x.device)
         scratch = _empty(M * O, x) if (act or p > 0.0) else None
-        check(lib.mtadgat_linear_bwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dx), 0,
-                                     dw.data_ptr(), db.data_ptr(), _ptr(scratch), M, I, O, act, p,
-                                     seed_t.data_ptr() if has_seed else None, rng_stream, _stream()))
+        _run_bwd(x.device, lambda parts, st: check(lib.mtadgat_linear_bwd(
+            x.data_ptr(), w.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dx), 0, dw.data_ptr(), db.data_ptr(),
+            _ptr(scratch), M, I, O, act, p, seed_t.data_ptr() if has_seed else None, rng_stream, parts, st)),
+            (x, y, dy, scratch, dw, db))
         return dx, dw, db, None, None, None, None
 
 
