@@ -316,24 +316,33 @@ __global__ void __launch_bounds__(256) gat_score_fwd_kernel(ScoreParams P) {
           for (int a = 0; a < MI; ++a)
 #pragma unroll
             for (int c = 0; c < MJ; ++c) { accp[a][c] = 0.f; accn[a][c] = 0.f; }
+          // RBp, JTp are multiples of 4 and the tiles are 16-byte aligned: operands come in as 16 / 8-byte vectors
+          auto ldv = [](const float* p, float (&v)[MI]) {
+            if constexpr (MI == 4) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+            else if constexpr (MI == 2) { float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+            else { v[0] = p[0]; }
+          };
+          auto ldq = [](const float* p, float (&v)[MJ]) {
+            if constexpr (MJ == 4) { float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+            else if constexpr (MJ == 2) { float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+            else { v[0] = p[0]; }
+          };
           int d = 0;
+#pragma unroll 2
           for (; d < dsplit; ++d) {
             float pv[MI], qv[MJ];
-#pragma unroll
-            for (int a = 0; a < MI; ++a) pv[a] = pp[d * RBp + a];
-#pragma unroll
-            for (int c = 0; c < MJ; ++c) qv[c] = qq[d * JTp + c];
+            ldv(pp + d * RBp, pv);
+            ldq(qq + d * JTp, qv);
 #pragma unroll
             for (int a = 0; a < MI; ++a)
 #pragma unroll
               for (int c = 0; c < MJ; ++c) accp[a][c] += fmaxf(pv[a] + qv[c], 0.f);
           }
+#pragma unroll 2
           for (; d < dt; ++d) {
             float pv[MI], qv[MJ];
-#pragma unroll
-            for (int a = 0; a < MI; ++a) pv[a] = pp[d * RBp + a];
-#pragma unroll
-            for (int c = 0; c < MJ; ++c) qv[c] = qq[d * JTp + c];
+            ldv(pp + d * RBp, pv);
+            ldq(qq + d * JTp, qv);
 #pragma unroll
             for (int a = 0; a < MI; ++a)
 #pragma unroll
@@ -605,8 +614,8 @@ static int pick_score_tiles(const GatDims& d, int& RB, int& JT, int& DT, size_t&
   if (ntd > 256) return -1;
   int rbmax = 4 * (256 / ntd);
   RB = min(d.K, rbmax);
-  // keep roughly >= 2 CTAs per window when K is large enough so small batches still fill the GPU
-  if (d.K >= 64) RB = min(RB, (d.K + 1) / 2);
+  // large K: split the rows so small batches still fill the GPU (K <= 128: one CTA owns the whole window)
+  if (d.K > 128) RB = min(RB, (d.K + 1) / 2);
   JT = d.K; DT = d.E > 0 ? d.E : 1;
   for (;;) {
     int RBp = (RB + 3) & ~3, JTp = (JT + 3) & ~3;

@@ -118,9 +118,32 @@ template <> struct OpA<Cat3AT> {
     return Ctx{b < f.B ? (long long)b * f.n + t : -1};
   }
   static __device__ __forceinline__ void load8(const Cat3AT& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    if (c.row < 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+      return;
+    }
+    if (((f.k0 | f.k1 | f.k2) & 1) == 0) {
+      // even slice widths: (row*width + even column) is 8-byte aligned and a pair never straddles two slices
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        int kk = k0 + j;
+        float2 t = make_float2(0.f, 0.f);
+        if (kk < kend) {
+          const float* p;
+          if (kk < f.k0) p = f.x0 + c.row * f.k0 + kk;
+          else if (kk < f.k0 + f.k1) p = f.x1 + c.row * f.k1 + (kk - f.k0);
+          else p = f.x2 + c.row * f.k2 + (kk - f.k0 - f.k1);
+          t = __ldg(reinterpret_cast<const float2*>(p));
+          if (kk + 1 >= kend) t.y = 0.f;
+        }
+        v[j] = t.x; v[j + 1] = t.y;
+      }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      v[j] = (c.row >= 0 && k0 + j < kend) ? cat3_load(f.x0, f.x1, f.x2, f.k0, f.k1, f.k2, c.row, k0 + j) : 0.f;
+      v[j] = (k0 + j < kend) ? cat3_load(f.x0, f.x1, f.x2, f.k0, f.k1, f.k2, c.row, k0 + j) : 0.f;
   }
 };
 template <> struct OpB<WT> {
@@ -290,30 +313,36 @@ __global__ void rep_dS_kernel(const float* __restrict__ dgi_t, const float* __re
   }
   dS[idx] = acc;
 }
-// dhsrc[b][m] (+)= sum_{t,j: m0[t]+j == m} sum_g dgi[b,t,g] S[t][j][g]
-// one warp per (tile, m): lane = (g parity, window) so every load of the tiled dgi is a full 64-byte line
-__global__ void rep_dh_kernel(const float* __restrict__ dgi_t, const float* __restrict__ S, int B, int n, int Hs, int G,
-                              int J, float* __restrict__ dh, int accumulate) {
-  const int ntiles = (B + 15) >> 4;
-  int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (wid >= ntiles * Hs) return;
-  const int m = wid % Hs, tile = wid / Hs;
-  const int w = lane & 15, gh = lane >> 4;
-  float acc = 0.f;
-  int tlo = (int)(((long long)max(m - J + 1, 0) * n) / Hs);
-  int thi = (int)min((long long)n - 1, (((long long)(m + 1) * n) / Hs));
-  for (int t = tlo; t <= thi; ++t) {
-    int j = m - (int)(((long long)t * Hs) / n);
-    if (j < 0 || j >= J) continue;
-    const float* s = S + ((long long)t * J + j) * G;
-    const float* d = dgi_t + (((size_t)tile * n + t) * G) * 16 + w;
-    for (int g = gh; g < G; g += 2) acc = fmaf(__ldg(d + (size_t)g * 16), __ldg(s + g), acc);
-  }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+// dhsrc[b][m] += sum_{t,j: m0[t]+j == m} sum_g dgi[b,t,g] S[t][j][g]
+// one 256-thread block per (tile, t): thread = (window, 1/16 of the gate range); every load of the tiled dgi is part
+// of a full 64-byte line; block reduction, then a handful of atomics per window (dh zeroed / pre-filled by caller)
+__global__ void __launch_bounds__(256) rep_dh_kernel(const float* __restrict__ dgi_t, const float* __restrict__ S, int B,
+                                                    int n, int Hs, int G, int J, float* __restrict__ dh) {
+  __shared__ float red[16][17];
+  const int t = blockIdx.x % n, tile = blockIdx.x / n;
+  const int w = threadIdx.x & 15, gq = threadIdx.x >> 4;
   const int b = tile * 16 + w;
-  if (gh == 0 && b < B) {
-    float* q = dh + (size_t)b * Hs + m;
-    *q = accumulate ? *q + acc : acc;
+  const int m0 = (int)(((long long)t * Hs) / n);
+  const float* d = dgi_t + (((size_t)tile * n + t) * G) * 16 + w;
+  for (int j = 0; j < J; ++j) {
+    if (m0 + j >= Hs) break;
+    const float* s = S + ((long long)t * J + j) * G;
+    float a0 = 0.f, a1 = 0.f;
+    int g = gq;
+    for (; g + 16 < G; g += 32) {
+      a0 = fmaf(__ldg(d + (size_t)g * 16), __ldg(s + g), a0);
+      a1 = fmaf(__ldg(d + (size_t)(g + 16) * 16), __ldg(s + g + 16), a1);
+    }
+    if (g < G) a0 = fmaf(__ldg(d + (size_t)g * 16), __ldg(s + g), a0);
+    red[gq][w] = a0 + a1;
+    __syncthreads();
+    if (gq == 0 && b < B) {
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += red[q][w];
+      atomicAdd(dh + (size_t)b * Hs + m0 + j, acc);
+    }
+    __syncthreads();
   }
 }
 
@@ -653,7 +682,8 @@ extern "C" int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const 
   if (parts & 1) {
     int rc = run_recurrence_bwd(gates, out, w_hh, dout, nullptr, gmax, dgi, dghn, B, n, R, s);
     if (rc) return rc;
-    rep_dh_kernel<<<cdiv((long long)(Bp / 16) * Hs, 8), 256, 0, s>>>(dgi, S, B, n, Hs, G, J, dh_src, dh_accumulate);
+    if (!dh_accumulate) MG_CUDA(cudaMemsetAsync(dh_src, 0, sizeof(float) * (size_t)B * Hs, s));
+    rep_dh_kernel<<<(Bp / 16) * n, 256, 0, s>>>(dgi, S, B, n, Hs, G, J, dh_src);
     MG_COUNT_LAUNCH();
   }
   if (parts & 2) {

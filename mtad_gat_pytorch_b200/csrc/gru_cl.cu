@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
     for (int t = 0; t < n; ++t) {
       long long q0 = clock64();
       if (t > 0) tc::mbar_wait(h_bar, (t - 1) & 1);
-      fence_proxy_async_all();
+      // h_t was written by st.async (async proxy, completion observed through the mbarrier): no generic->async
+      // proxy fence is needed before the MMAs read it
       tc::tc_fence_after();
       long long q1 = clock64();
       c_wait += q1 - q0;
@@ -401,7 +402,6 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
     __syncwarp();
     for (int it = 0; it < n - 1; ++it) {
       tc::mbar_wait(h_bar, it & 1);
-      fence_proxy_async_all();
       tc::tc_fence_after();
       const uint64_t bd0 = tc::make_smem_desc(tc::smem_u32(sB) + (uint32_t)((it & 1) * KC * LBO_B), LBO_B, SBO_B);
       uint32_t alo = alo0, blo = (uint32_t)bd0;
