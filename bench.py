@@ -184,8 +184,11 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         last = None
+        step.prefetch_host(xs_host[0], ys_host[0])
         for i in range(args.steps):
-            last = step.run_host(xs_host[i % n_host], ys_host[i % n_host])
+            if i + 1 < args.steps:       # H2D of the next batch overlaps this step; one H2D + one D2H per step
+                step.prefetch_host(xs_host[(i + 1) % n_host], ys_host[(i + 1) % n_host])
+            last = step.run_prefetched()
         barrier()
         e2e_s = (time.perf_counter() - t0) / args.steps
     t_ms = torch.tensor([ms_dev, e2e_s * 1e3], dtype=torch.float64, device=dev)

@@ -535,34 +535,36 @@ __global__ void __launch_bounds__(256) gat_bwd1_kernel(Bwd1Params P) {
 // ---------------------------------------------------------------------------------------------
 struct Bwd2Params {
   const float* pqt; const float* de; const int* meta; float* dpqt;
-  int K, Kp, E, NC, DT, v2, pass; float alpha;
+  int K, Kp, E, NC, DT, RBk, v2, pass; float alpha;      // RBk: rows r per CTA (multiple of 4)
 };
 
+// grid: (channel tiles, row blocks, B)
 __global__ void __launch_bounds__(256) gat_bwd2_kernel(Bwd2Params P) {
   extern __shared__ __align__(16) float smem[];
-  const int b = blockIdx.z, d0 = blockIdx.x * P.DT;
-  const int K = P.K, Kp = P.Kp, E = P.E;
+  const int b = blockIdx.z, d0 = blockIdx.x * P.DT, r0 = blockIdx.y * P.RBk;
+  const int K = P.K, Kp = P.Kp, E = P.E, RBk = P.RBk;
+  const int rbk = min(RBk, Kp - r0);          // rows handled here (multiple of 4; rows >= K are padding)
   const int tid = threadIdx.x, nth = blockDim.x;
-  float* sW = smem;                         // [K (c)][Kp (r)]
-  float* sY = sW + (size_t)K * Kp;          // [DT+1][Kp]  (row DT = rank-1 channel of Y)
+  float* sW = smem;                         // [K (c)][RBk (r local)]
+  float* sY = sW + (size_t)K * RBk;         // [DT+1][Kp]  (row DT = rank-1 channel of Y)
   const float* pq = P.pqt + (size_t)b * P.NC * Kp;
   const float* de = P.de + (size_t)b * K * Kp;
   const int xoff = P.pass ? E : 0, yoff = P.pass ? 0 : E;
   const int x1 = 2 * E + P.pass, y1 = 2 * E + 1 - P.pass;
   const int dt = max(0, min(P.DT, E - d0));
-  // stage w as [c][r]
+  // stage w as [c][r local]
   if (P.pass == 0) {
-    for (int idx = tid; idx < K * Kp; idx += nth) {
-      int r = idx / Kp, c = idx - r * Kp;     // coalesced read of de[r][c]
-      if (c < K) sW[c * Kp + r] = de[r * Kp + c];
-    }
-    // zero the pad columns r in [K,Kp)
-    for (int idx = tid; idx < K * (Kp - K); idx += nth) {
-      int c = idx / (Kp - K), r = K + idx - c * (Kp - K);
-      sW[c * Kp + r] = 0.f;
+    // w(r,c) = de[r][c]: read rows r coalesced along c, write transposed
+    for (int idx = tid; idx < rbk * Kp; idx += nth) {
+      int rl = idx / Kp, c = idx - rl * Kp;
+      if (c < K) sW[c * RBk + rl] = (r0 + rl < K) ? de[(size_t)(r0 + rl) * Kp + c] : 0.f;
     }
   } else {
-    for (int idx = tid; idx < K * Kp; idx += nth) sW[idx] = de[idx];   // c = i rows, r = j columns
+    // w(r,c) = de[c][r]: rows c, contiguous along r
+    for (int idx = tid; idx < K * rbk; idx += nth) {
+      int c = idx / rbk, rl = idx - c * rbk;
+      sW[c * RBk + rl] = de[(size_t)c * Kp + r0 + rl];
+    }
   }
   for (int idx = tid; idx < dt * Kp; idx += nth) {
     int d = idx / Kp, c = idx - d * Kp;
@@ -571,33 +573,34 @@ __global__ void __launch_bounds__(256) gat_bwd2_kernel(Bwd2Params P) {
   for (int c = tid; c < Kp; c += nth) sY[P.DT * Kp + c] = pq[(size_t)y1 * Kp + c];
   __syncthreads();
   const int npos = P.v2 ? P.meta[0] : 0;
-  const int nrg = Kp >> 2;
+  const int nrg = rbk >> 2;
   const int nitems = nrg * dt;
   float* dpq = P.dpqt + (size_t)b * P.NC * Kp;
   for (int it = tid; it < nitems; it += nth) {
     int d = it / nrg, rg = it - d * nrg;
-    float4 xv = *reinterpret_cast<const float4*>(pq + (size_t)(xoff + d0 + d) * Kp + rg * 4);
+    float4 xv = *reinterpret_cast<const float4*>(pq + (size_t)(xoff + d0 + d) * Kp + r0 + rg * 4);
     const float* yrow = sY + d * Kp;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     for (int c = 0; c < K; ++c) {
       float y = yrow[c];
-      float4 w = *reinterpret_cast<const float4*>(sW + c * Kp + rg * 4);
+      float4 w = *reinterpret_cast<const float4*>(sW + c * RBk + rg * 4);
       a0 += (xv.x + y > 0.f) ? w.x : 0.f;
       a1 += (xv.y + y > 0.f) ? w.y : 0.f;
       a2 += (xv.z + y > 0.f) ? w.z : 0.f;
       a3 += (xv.w + y > 0.f) ? w.w : 0.f;
     }
     float sg = (d0 + d < npos) ? 1.f : -1.f;
-    *reinterpret_cast<float4*>(dpq + (size_t)(xoff + d0 + d) * Kp + rg * 4) = make_float4(sg * a0, sg * a1, sg * a2, sg * a3);
+    *reinterpret_cast<float4*>(dpq + (size_t)(xoff + d0 + d) * Kp + r0 + rg * 4) = make_float4(sg * a0, sg * a1, sg * a2, sg * a3);
   }
   if (blockIdx.x == 0) {
     const float* yrow = sY + P.DT * Kp;
-    for (int r = tid; r < Kp; r += nth) {
+    for (int rl = tid; rl < rbk; rl += nth) {
+      const int r = r0 + rl;
       float acc = 0.f;
       if (r < K) {
         float xr = pq[(size_t)x1 * Kp + r];
         for (int c = 0; c < K; ++c) {
-          float w = sW[c * Kp + r];
+          float w = sW[c * RBk + rl];
           float g = P.v2 ? P.alpha : ((xr + yrow[c] > 0.f) ? 1.f : P.alpha);
           acc = fmaf(w, g, acc);
         }
@@ -740,23 +743,21 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
   }
   // ---- bwd2 (two passes) ----
   if (do_data) {
-    int DT = d.E > 0 ? d.E : 1;
-    size_t smem;
-    for (;;) {
-      smem = sizeof(float) * ((size_t)d.K * d.Kp + (size_t)(DT + 1) * d.Kp);
-      if (smem <= 200 * 1024 || DT <= 8) break;
-      DT = (DT + 1) / 2;
-    }
+    // shared memory: de block [K][RBk] + Y tile [DT+1][Kp]; shrink the channel tile first, then the row block
+    int DT = d.E > 0 ? d.E : 1, RBk = d.Kp;
+    auto need = [&](int dtv, int rbv) { return sizeof(float) * ((size_t)d.K * rbv + (size_t)(dtv + 1) * d.Kp); };
+    while (need(DT, RBk) > 200 * 1024 && DT > 8) DT = (DT + 1) / 2;
+    while (need(DT, RBk) > 200 * 1024 && RBk > 16) RBk = (((RBk + 1) / 2) + 3) & ~3;
+    MG_CHECK_ARG(need(DT, RBk) <= 220 * 1024, "gat_bwd: K=%d too large", d.K);
     // more CTAs when the batch is small: split channels further
-    while ((long long)cdiv(max(d.E, 1), DT) * B < 296 && DT > 16) DT = (DT + 1) / 2;
-    smem = sizeof(float) * ((size_t)d.K * d.Kp + (size_t)(DT + 1) * d.Kp);
-    MG_CHECK_ARG(smem <= 220 * 1024, "gat_bwd: K=%d too large for the de tile", d.K);
+    while ((long long)cdiv(max(d.E, 1), DT) * cdiv(d.Kp, RBk) * B < 296 && DT > 16) DT = (DT + 1) / 2;
+    size_t smem = need(DT, RBk);
     cudaFuncSetAttribute(gat_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int pass = 0; pass < 2; ++pass) {
       Bwd2Params P;
       P.pqt = pqt; P.de = de; P.meta = meta; P.dpqt = dpqt; P.K = d.K; P.Kp = d.Kp; P.E = d.E; P.NC = d.NC;
-      P.DT = DT; P.v2 = use_gatv2; P.pass = pass; P.alpha = alpha;
-      gat_bwd2_kernel<<<dim3(max(1, cdiv(d.E, DT)), 1, B), 256, smem, s>>>(P);
+      P.DT = DT; P.RBk = RBk; P.v2 = use_gatv2; P.pass = pass; P.alpha = alpha;
+      gat_bwd2_kernel<<<dim3(max(1, cdiv(d.E, DT)), cdiv(d.Kp, RBk), B), 256, smem, s>>>(P);
       MG_COUNT_LAUNCH();
     }
   }

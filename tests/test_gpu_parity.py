@@ -325,6 +325,31 @@ def test_full_size_forward_properties(cfgname, k, n, out_dim, B):
     assert e1 < TOL and e2 < TOL
 
 
+@pytest.mark.parametrize("cfgname,k,n", [("c4", 512, 100), ("c5", 38, 512)])
+def test_large_shape_backward_vs_oracle(cfgname, k, n):
+    """BASELINE.json configs[3]/[4] shapes (k=512 feature GAT / n=512 temporal GAT): forward + every gradient
+    of a 2-window batch against the (fp32, memory-bound) oracle."""
+    import mtad_gat_pytorch_b200 as mg
+    mg.set_mode("fp32")
+    kwargs = dict(n_features=k, window_size=n, out_dim=k, forecast_n_layers=3, dropout=0.3)
+    cfg = orc.Config(**kwargs)
+    params = orc.make_params(cfg, seed=60, dtype=np.float32)
+    x, y = inputs_for(cfg, 2, 60)
+    x, y = x.astype(np.float32), y.astype(np.float32)
+    _, _, _, p_ref, r_ref, dx_ref, g_ref = orc.loss_fwd_bwd(x, y, params, cfg)
+    m = build(kwargs, params)
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    preds, recons = m(xt)
+    loss_fn(xt, torch.from_numpy(y).cuda(), preds, recons, None).backward()
+    errs = {"preds": rel(preds, p_ref), "recons": rel(recons, r_ref), "dx": rel(xt.grad, dx_ref)}
+    for pname, p in m.named_parameters():
+        errs["grad." + pname] = rel(p.grad, g_ref[pname])
+    worst = max(errs, key=errs.get)
+    print(f"[{cfgname} bwd] worst {worst} = {errs[worst]:.3e}")
+    bad = {k_: e for k_, e in errs.items() if not e < TOL}
+    assert not bad, bad
+
+
 def test_full_size_c2_backward_properties():
     """C2 (k=38,n=100,B=256) backward: the backward map is linear in the output gradient and parameter
     gradients are sums over windows -- checked exactly as split-batch consistency and linearity."""
