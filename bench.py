@@ -31,6 +31,11 @@ MODEL_KW = dict(n_features=K_FEAT, window_size=N_WIN, out_dim=OUT_DIM, forecast_
 WORKLOAD = "SMD-shape (k=38,n=100) MTAD_GAT train step fwd+bwd+Adam, batch 256/GPU, fp32"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload, from the `ncu --set full` capture
+# summarised in profiles/ (cold caches: ncu flushes L2 before every replay pass)
+NCU_TRAFFIC = {}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -140,6 +145,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+    if args.gru_split:
+        mg.set_gru_split(args.gru_split)
     torch.manual_seed(0)
     model = mg.MTAD_GAT(**MODEL_KW).to(dev)
     model.train()
@@ -200,7 +207,12 @@ def run_ours(args):
         peaks = load_peaks()
         from mtad_gat_pytorch_b200 import kernel_bench
         kern = kernel_bench.stage_rooflines(model, B, peaks, dev)
-        dominant = max(kern, key=lambda r: r["ms"])
+        # dominant single kernel = the slower of the two persistent recurrence launches (largest share of the step,
+        # profiles/r1_launches_bench.csv); the other rows are whole stages (several launches each)
+        single = [r for r in kern if r.get("single_kernel")]
+        dominant = max(single or kern, key=lambda r: r["ms"])
+        if B == BATCH and dominant["kernel"] in NCU_TRAFFIC:
+            dominant["traffic"] = NCU_TRAFFIC[dominant["kernel"]]
         roof = {k_: dominant[k_] for k_ in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
         roof["kernel"] = dominant["kernel"]
         roof["peak_src"] = peaks["src"]
@@ -236,6 +248,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--gru-split", type=int, default=0, help="clusters per 16-window tile in the recurrence (0 = auto)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -98,10 +98,28 @@ int mtadgat_linear_bwd(const float* x, const float* w, const float* y, const flo
  *      128 x N x K product through the same shared-memory operand layout (diagnostic / unit test). ---- */
 int mtadgat_set_gru_impl(int impl);
 int mtadgat_get_gru_impl(void);
+/* cluster recurrence: clusters per 16-window tile, 0 = auto (default; small batches split a tile over 2 or 4
+ * clusters so that more SMs work on the serial chain), or 1 / 2 / 4.  Results do not depend on it. */
+int mtadgat_set_gru_split(int split);
+/* The recurrence alone (torch.nn.GRU's per-step part, modules.py:235-238) on WINDOW-TILED internals
+ * T[b/16][t][channel][b%16] (B rounded up to 16): gi_t = x W_ih^T + b_ih (channels 3H), gates_t (4H: r,z,n,h_n),
+ * dgi_t (3H), dghn_t (H).  mtadgat_gru_fwd / _bwd = projection GEMMs + these.  wt_scratch: 3H*H floats;
+ * gmax_word: one device word.  bench.py times these entry points for the per-kernel roofline. */
+int mtadgat_gru_recurrence_fwd(const float* gi_t, const float* w_hh, const float* b_hh, float* wt_scratch, float* out,
+                               float* h_last /*nullable*/, float* gates_t /*nullable*/, int B, int n, int H, void* stream);
+int mtadgat_gru_recurrence_bwd(const float* gates_t, const float* out, const float* w_hh, const float* dout /*nullable*/,
+                               const float* dh_last /*nullable*/, float* dgi_t, float* dghn_t, unsigned int* gmax_word,
+                               int B, int n, int H, void* stream);
 /* GEMM-shaped stages (conv, projections, heads, weight gradients): 1 (default) = tcgen05 kind::f16 on bf16 hi/lo splits
- * (bf16x3, ~1e-5 relative), 0 = SIMT fp32. */
+ * (bf16x3, ~1e-5 relative) from operands packed into a per-stream workspace, 2 = same arithmetic with the operand
+ * gather inside the GEMM kernel (no workspace), 0 = SIMT fp32. */
 int mtadgat_set_gemm_impl(int impl);
 int mtadgat_get_gemm_impl(void);
+/* The packed-operand GEMM keeps ONE grow-only device buffer per stream it is called on (the only memory the library
+ * owns).  It grows on demand, except while the stream is being captured into a CUDA graph: run the same call eagerly
+ * once on that stream first, or reserve it here.  _release frees every buffer (synchronises the device). */
+int mtadgat_workspace_reserve(void* stream, long long bytes);
+void mtadgat_workspace_release(void);
 int mtadgat_tc_probe(const float* A, const float* Bm, float* D, int Mtot, int row0, int K, int N, int b_mn_major,
                      int mma_m, void* stream);
 void mtadgat_gru_debug_buffer(long long* dev_ptr);   /* optional: 16 int64 per-phase cycle counters of the cluster GRU */

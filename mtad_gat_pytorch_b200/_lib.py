@@ -42,8 +42,13 @@ SIGNATURES = {
     "mtadgat_linear_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _P, _U, _I, _P]),
     "mtadgat_set_gemm_impl": (_I, [_I]),
     "mtadgat_get_gemm_impl": (_I, []),
+    "mtadgat_workspace_reserve": (_I, [_P, _LL]),
+    "mtadgat_workspace_release": (None, []),
     "mtadgat_set_gru_impl": (_I, [_I]),
     "mtadgat_get_gru_impl": (_I, []),
+    "mtadgat_set_gru_split": (_I, [_I]),
+    "mtadgat_gru_recurrence_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "mtadgat_gru_recurrence_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mtadgat_tc_probe": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mtadgat_gru_debug_buffer": (None, [_P]),
     "mtadgat_tc_mma_bench": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

@@ -6,7 +6,55 @@
 
 static thread_local char g_err[512] = "";
 unsigned long long g_mtadgat_launches = 0;
-int g_mtadgat_gemm_impl = 1;   // 1 = tcgen05 bf16x3 GEMMs (tc_gemm.cuh), 0 = SIMT fp32 (gemm.cuh)
+int g_mtadgat_gemm_impl = 1;   // 1 = packed-operand tcgen05 bf16x3 GEMMs (tc_gemm2.cuh), 2 = in-kernel gather variant
+                               // (tc_gemm.cuh), 0 = SIMT fp32 (gemm.cuh)
+static thread_local int g_pending_rc = 0;
+void mtadgat_set_pending_error(int rc) { if (!g_pending_rc) g_pending_rc = rc; }
+int mtadgat_take_pending_error(void) { int r = g_pending_rc; g_pending_rc = 0; return r; }
+
+// ---- pack workspace: one grow-only device buffer per stream (kernels of one stream run in order, so a buffer is
+//      never rewritten while an earlier GEMM of the same stream still reads it) ----
+namespace {
+struct WsSlot { cudaStream_t s; uint8_t* p; size_t bytes; bool used; };
+WsSlot g_ws[32];
+}
+uint8_t* mtadgat_workspace(cudaStream_t s, size_t bytes) {
+  WsSlot* slot = nullptr;
+  for (auto& w : g_ws) if (w.used && w.s == s) { slot = &w; break; }
+  if (slot && slot->bytes >= bytes) return slot->p;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &st);
+  if (st != cudaStreamCaptureStatusNone) {
+    mtadgat_set_error("GEMM pack workspace of this stream is %zu bytes but %zu are needed, and it cannot grow while the "
+                      "stream is being captured: run the step eagerly once on the same streams before capture, or call "
+                      "mtadgat_workspace_reserve", slot ? slot->bytes : (size_t)0, bytes);
+    return nullptr;
+  }
+  if (!slot) {
+    for (auto& w : g_ws) if (!w.used) { slot = &w; break; }
+    if (!slot) { mtadgat_set_error("workspace: more than 32 distinct streams"); return nullptr; }
+    slot->used = true; slot->s = s; slot->p = nullptr; slot->bytes = 0;
+  }
+  if (slot->p) { cudaStreamSynchronize(s); cudaFree(slot->p); slot->p = nullptr; slot->bytes = 0; }
+  size_t want = bytes + bytes / 4 + (1u << 20);
+  cudaError_t e = cudaMalloc(&slot->p, want);
+  if (e != cudaSuccess) {
+    mtadgat_set_error("workspace: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    slot->p = nullptr;
+    return nullptr;
+  }
+  slot->bytes = want;
+  return slot->p;
+}
+extern "C" int mtadgat_workspace_reserve(void* stream, long long bytes) {
+  MG_CHECK_ARG(bytes >= 0, "workspace_reserve: negative size");
+  if (!mtadgat_workspace((cudaStream_t)stream, (size_t)bytes)) return MTADGAT_ERR_CUDA;
+  return MTADGAT_OK;
+}
+extern "C" void mtadgat_workspace_release(void) {
+  cudaDeviceSynchronize();
+  for (auto& w : g_ws) if (w.used) { if (w.p) cudaFree(w.p); w = WsSlot{}; }
+}
 
 void mtadgat_set_error(const char* fmt, ...) {
   va_list ap;
@@ -20,7 +68,7 @@ extern "C" int mtadgat_abi_version(void) { return MTADGAT_ABI_VERSION; }
 extern "C" unsigned long long mtadgat_launch_count(void) { return g_mtadgat_launches; }
 extern "C" void mtadgat_reset_launch_count(void) { g_mtadgat_launches = 0; }
 extern "C" int mtadgat_set_gemm_impl(int impl) {
-  MG_CHECK_ARG(impl == 0 || impl == 1, "set_gemm_impl: 0 (SIMT fp32) or 1 (tcgen05 bf16x3)");
+  MG_CHECK_ARG(impl >= 0 && impl <= 2, "set_gemm_impl: 0 (SIMT fp32), 1 (tcgen05 bf16x3, packed operands) or 2 (tcgen05 bf16x3, in-kernel gather)");
   g_mtadgat_gemm_impl = impl;
   return MTADGAT_OK;
 }

@@ -10,6 +10,7 @@
 #define MTADGAT_ERR_UNSUPPORTED 3
 
 void mtadgat_set_error(const char* fmt, ...);
+int mtadgat_take_pending_error(void);    // error recorded by a launch helper that cannot return a code (0 = none)
 
 #define MG_CHECK_ARG(cond, ...)                 \
   do {                                          \
@@ -21,6 +22,8 @@ void mtadgat_set_error(const char* fmt, ...);
 
 #define MG_CHECK_LAUNCH(name)                                                      \
   do {                                                                             \
+    int p__ = mtadgat_take_pending_error();                                        \
+    if (p__) return p__;                                                           \
     cudaError_t e__ = cudaGetLastError();                                          \
     if (e__ != cudaSuccess) {                                                      \
       mtadgat_set_error("%s: CUDA error %s", name, cudaGetErrorString(e__));       \

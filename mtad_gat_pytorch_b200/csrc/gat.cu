@@ -217,6 +217,12 @@ struct WpB {
   const float* wp; int NC;
   __device__ __forceinline__ float operator()(int, int c, int dd) const { return __ldg(wp + (long long)dd * NC + c); }
 };
+}  // namespace
+namespace tcg2 {
+template <> struct BatchInvariant<WpT> { static constexpr bool value = true; };     // weights: packed once, not per window
+template <> struct BatchInvariant<WpB> { static constexpr bool value = true; };
+}
+namespace {
 template <bool FEATURE>
 struct StNodeAcc {
   float* dx; int n, k; int accumulate;

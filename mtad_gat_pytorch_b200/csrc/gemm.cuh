@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include "tc_gemm2.cuh"
 
 enum { ACT_NONE = 0, ACT_RELU = 1, ACT_SIGMOID = 2 };
 
@@ -140,7 +141,8 @@ template <class AL, class BL, class CS>
 static inline void launch_gemm_batched(int batch, int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s) {
   if (M <= 0 || N <= 0 || batch <= 0) return;
   // dispatch must not depend on the batch-derived dimension M: a window's result may not depend on its batch
-  if (g_mtadgat_gemm_impl == 1 && N >= 16 && K >= 16) { tcg::launch_batched(batch, M, N, K, A, Bm, C, s); return; }
+  if (g_mtadgat_gemm_impl == 1 && N >= 16 && K >= 16) { tcg2::launch_batched(batch, M, N, K, A, Bm, C, s); return; }
+  if (g_mtadgat_gemm_impl == 2 && N >= 16 && K >= 16) { tcg::launch_batched(batch, M, N, K, A, Bm, C, s); return; }
   dim3 g(cdiv(N, GEMM_BN), cdiv(M, GEMM_BM), batch);
   gemm_kernel<AL, BL, CS><<<g, 256, 0, s>>>(M, N, K, K, 0, A, Bm, C);
   MG_COUNT_LAUNCH();
@@ -150,7 +152,8 @@ static inline void launch_gemm_batched(int batch, int M, int N, int K, AL A, BL 
 template <class AL, class BL, class CS>
 static inline void launch_gemm_splitk(int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s, int target_ctas = 592) {
   if (M <= 0 || N <= 0) return;
-  if (g_mtadgat_gemm_impl == 1 && M >= 32 && N >= 16) { tcg::launch_splitk(M, N, K, A, Bm, C, s, 296); return; }
+  if (g_mtadgat_gemm_impl == 1 && M >= 32 && N >= 16) { tcg2::launch_splitk(M, N, K, A, Bm, C, s, 296); return; }
+  if (g_mtadgat_gemm_impl == 2 && M >= 32 && N >= 16) { tcg::launch_splitk(M, N, K, A, Bm, C, s, 296); return; }
   int tiles = cdiv(N, GEMM_BN) * cdiv(M, GEMM_BM);
   int splits = max(1, min(cdiv(K, 4 * GEMM_BK), cdiv(target_ctas, tiles)));
   int klen = cdiv(cdiv(K, splits), GEMM_BK) * GEMM_BK;

@@ -573,6 +573,29 @@ extern "C" int mtadgat_set_gru_impl(int impl) {
 }
 extern "C" int mtadgat_get_gru_impl(void) { return g_gru_impl; }
 
+extern "C" int mtadgat_gru_recurrence_fwd(const float* gi_t, const float* w_hh, const float* b_hh, float* wt_scratch,
+                                          float* out, float* h_last, float* gates_t, int B, int n, int H, void* stream) {
+  MG_CHECK_ARG(gi_t && w_hh && b_hh && wt_scratch && (out || h_last), "gru_recurrence_fwd: null pointer");
+  MG_CHECK_ARG(B > 0 && n > 0 && H > 0, "gru_recurrence_fwd: bad shape");
+  MG_CHECK_ARG(!gates_t || out, "gru_recurrence_fwd: saving gates needs the per-step outputs");
+  int rc = run_recurrence_fwd(gi_t, nullptr, nullptr, nullptr, 0, 0, w_hh, b_hh, wt_scratch, out, h_last, gates_t, B, n, H,
+                              (cudaStream_t)stream);
+  if (rc) return rc;
+  MG_CHECK_LAUNCH("gru_recurrence_fwd");
+  return MTADGAT_OK;
+}
+extern "C" int mtadgat_gru_recurrence_bwd(const float* gates_t, const float* out, const float* w_hh, const float* dout,
+                                          const float* dh_last, float* dgi_t, float* dghn_t, unsigned int* gmax_word,
+                                          int B, int n, int H, void* stream) {
+  MG_CHECK_ARG(gates_t && out && w_hh && dgi_t && dghn_t && gmax_word, "gru_recurrence_bwd: null pointer");
+  MG_CHECK_ARG(dout || dh_last, "gru_recurrence_bwd: need dout and/or dh_last");
+  MG_CHECK_ARG(B > 0 && n > 0 && H > 0, "gru_recurrence_bwd: bad shape");
+  int rc = run_recurrence_bwd(gates_t, out, w_hh, dout, dh_last, gmax_word, dgi_t, dghn_t, B, n, H, (cudaStream_t)stream);
+  if (rc) return rc;
+  MG_CHECK_LAUNCH("gru_recurrence_bwd");
+  return MTADGAT_OK;
+}
+
 // saved (floats): wt (3H*H, padded to 4) | gates_t (Bp*n*4H, only if save)
 extern "C" long long mtadgat_gru_saved_floats(int B, int n, int H, int save) {
   return (long long)(al4((size_t)3 * H * H) + (save ? (size_t)tiled_B(B) * n * 4 * H : 0));

@@ -102,6 +102,64 @@ static bool cl_geom(int H, ClGeom& g) {
   return false;
 }
 
+// W consecutive floats (W = 1, 2, 4; pointer aligned to 4*W bytes)
+template <int W> __device__ __forceinline__ void ldg_w(const float* p, float* v);
+template <> __device__ __forceinline__ void ldg_w<4>(const float* p, float* v) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+template <> __device__ __forceinline__ void ldg_w<2>(const float* p, float* v) {
+  float2 a = __ldg(reinterpret_cast<const float2*>(p)); v[0] = a.x; v[1] = a.y;
+}
+template <> __device__ __forceinline__ void ldg_w<1>(const float* p, float* v) { v[0] = __ldg(p); }
+template <int W> __device__ __forceinline__ void ld_w(const float* p, float* v);
+template <> __device__ __forceinline__ void ld_w<4>(const float* p, float* v) {
+  float4 a = *reinterpret_cast<const float4*>(p); v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+}
+template <> __device__ __forceinline__ void ld_w<2>(const float* p, float* v) {
+  float2 a = *reinterpret_cast<const float2*>(p); v[0] = a.x; v[1] = a.y;
+}
+template <> __device__ __forceinline__ void ld_w<1>(const float* p, float* v) { v[0] = *p; }
+template <int W> __device__ __forceinline__ void st_w(float* p, const float* v);
+template <> __device__ __forceinline__ void st_w<4>(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void st_w<2>(float* p, const float* v) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+template <> __device__ __forceinline__ void st_w<1>(float* p, const float* v) { *p = v[0]; }
+
+// Hand a thread quad's fp16 values (unit u; thread wq of the quad owns WPT consecutive windows, scaled by `sc`) to
+// every CTA of the cluster: the quad's lanes merge their values with shuffles so that ONE asynchronous store per
+// 8 windows carries them, completing its bytes on the destination CTA's mbarrier.  `off` = byte offset of
+// (unit row, window 0) inside the destination B buffer.  All 32 lanes must call this.
+template <int WPT>
+__device__ __forceinline__ void send_quad(const float* v, float sc, bool valid, int wq, uint32_t buf_addr, uint32_t off,
+                                          uint32_t hbar_addr, int CS) {
+  if (WPT == 4) {
+    const uint32_t p0 = pack_h2(sat_h(v[0] * sc), sat_h(v[1] * sc)), p1 = pack_h2(sat_h(v[2] * sc), sat_h(v[3] * sc));
+    const uint32_t o0 = __shfl_xor_sync(0xffffffffu, p0, 1), o1 = __shfl_xor_sync(0xffffffffu, p1, 1);
+    if (valid && !(wq & 1)) {
+      const uint32_t dst = buf_addr + off + (uint32_t)(wq >> 1) * SBO_B;
+      for (int r = 0; r < CS; ++r) st_async_v4(mapa(dst, (uint32_t)r), p0, p1, o0, o1, mapa(hbar_addr, (uint32_t)r));
+    }
+  } else if (WPT == 2) {
+    const uint32_t p0 = pack_h2(sat_h(v[0] * sc), sat_h(v[1] * sc));
+    const uint32_t p1 = __shfl_down_sync(0xffffffffu, p0, 1), p2 = __shfl_down_sync(0xffffffffu, p0, 2),
+                   p3 = __shfl_down_sync(0xffffffffu, p0, 3);
+    if (valid && wq == 0) {
+      const uint32_t dst = buf_addr + off;
+      for (int r = 0; r < CS; ++r) st_async_v4(mapa(dst, (uint32_t)r), p0, p1, p2, p3, mapa(hbar_addr, (uint32_t)r));
+    }
+  } else {
+    const uint32_t p0 = (uint32_t)__half_as_ushort(__float2half_rn(sat_h(v[0] * sc)));
+    const uint32_t p1 = __shfl_down_sync(0xffffffffu, p0, 1), p2 = __shfl_down_sync(0xffffffffu, p0, 2),
+                   p3 = __shfl_down_sync(0xffffffffu, p0, 3);
+    if (valid && wq == 0) {
+      const uint32_t dst = buf_addr + off;
+      for (int r = 0; r < CS; ++r)
+        st_async_v2(mapa(dst, (uint32_t)r), p0 | (p1 << 16), p2 | (p3 << 16), mapa(hbar_addr, (uint32_t)r));
+    }
+  }
+}
+
 // ==========================================================================================================
 // forward
 // ==========================================================================================================
@@ -120,7 +178,13 @@ static size_t cl_fwd_smem(int H, int Hs_rep) {
   return (size_t)KC * 128 * 16 + 2 * (size_t)KC * LBO_B + (size_t)128 * SG_LD * 4 + (size_t)NB * Hs_rep * 4 + 128;
 }
 
-__global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P) {
+// WPT = windows per epilogue thread; one cluster advances NW = 4*WPT windows (a 16/NW-th of a 16-window tile).
+// Small batches use small NW: more clusters (more SMs busy, or two clusters interleaving on one SM) and a shorter
+// per-step dependency chain; the MMA is operand-fetch bound, so its cost does not depend on how many of the 16
+// B-operand columns carry live windows.
+template <int WPT>
+__global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P) {
+  constexpr int NW = 4 * WPT, SPLIT = NB / NW;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int H = P.H, G = 3 * H, n = P.n, CS = P.CS, Uc = P.Uc;
   const int Kp = (CS * Uc + 15) & ~15, KC = Kp / 8;
@@ -128,7 +192,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
   uint8_t* sA = smem_raw;                                   // [KC][128 rows][16 B]
   uint8_t* sB = sA + (size_t)KC * lboA;                     // [2][KC][256 B]
   float* sG = reinterpret_cast<float*>(sB + 2 * (size_t)KC * LBO_B);     // [128][SG_LD]
-  float* sHs = sG + 128 * SG_LD;                            // rep mode: h_src tile [16][Hs]
+  float* sHs = sG + 128 * SG_LD;                            // rep mode: h_src rows of this cluster's windows [NW][Hs]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sHs) +
                                                (P.gi ? 0 : (((size_t)NB * P.Hs * 4 + 15) & ~(size_t)15)));
   uint64_t* acc_bar = bars;        // local: MMA commit -> epilogue
@@ -136,7 +200,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_ctarank();
-  const int tile = blockIdx.x / CS, b0 = tile * NB;
+  const int cid = blockIdx.x / CS;
+  const int tile = cid / SPLIT, wo = (cid % SPLIT) * NW, b0 = tile * NB + wo;     // b0 = first window of this cluster
   const int u0 = rank * Uc, nu = max(0, min(Uc, H - u0));
 
   // ---- one-time staging: this CTA's W_hh rows (3 gates x Uc units) -> fp16 canonical layout; h_0 = 0 ----
@@ -148,7 +213,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
   }
   for (int idx = tid; idx < (2 * KC * LBO_B) / 4; idx += CL_THREADS) reinterpret_cast<uint32_t*>(sB)[idx] = 0u;
   if (!P.gi)
-    for (int idx = tid; idx < NB * P.Hs; idx += CL_THREADS) {
+    for (int idx = tid; idx < NW * P.Hs; idx += CL_THREADS) {
       int w = idx / P.Hs, m = idx - w * P.Hs;
       sHs[idx] = (b0 + w < P.B) ? __ldg(P.hsrc + (size_t)(b0 + w) * P.Hs + m) : 0.f;
     }
@@ -172,7 +237,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
     const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
     const uint32_t ainc = (uint32_t)(2 * lboA) >> 4, binc = (uint32_t)(2 * LBO_B) >> 4;
     const int nkc = Kp / 16;
-    const uint32_t tx_bytes = (uint32_t)H * NB * 2;          // the whole h_t (all CTAs' slices) lands in this buffer
+    const uint32_t tx_bytes = (uint32_t)H * NW * 2;          // the whole h_t (all CTAs' slices) lands in this buffer
     long long c_wait = 0, c_issue = 0;
     for (int t = 0; t < n; ++t) {
       long long q0 = clock64();
@@ -198,8 +263,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
     }
     if (P.dbg && blockIdx.x == 0 && lane == 0) { P.dbg[0] = c_wait / n; P.dbg[1] = c_issue / n; }
   } else {
-    // ================= epilogue: thread = (local unit i, 4 windows) =================
-    const int i = tid >> 2, wq = tid & 3, wb = 4 * wq;
+    // ================= epilogue: thread = (local unit i, WPT windows) =================
+    const int i = tid >> 2, wq = tid & 3, wb = WPT * wq;
     const bool valid = i < nu;
     const int u = u0 + i;
     float bhr = 0.f, bhz = 0.f, bhn = 0.f, bir = 0.f, biz = 0.f, bin = 0.f;
@@ -207,45 +272,52 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
       bhr = __ldg(P.b_hh + u); bhz = __ldg(P.b_hh + H + u); bhn = __ldg(P.b_hh + 2 * H + u);
       if (!P.gi) { bir = __ldg(P.b_ih + u); biz = __ldg(P.b_ih + H + u); bin = __ldg(P.b_ih + 2 * H + u); }
     }
-    float h[4] = {0.f, 0.f, 0.f, 0.f};
-    // byte offset of (unit u, windows wb..wb+3) inside one B buffer
-    const uint32_t hoff = (uint32_t)(u >> 3) * LBO_B + (uint32_t)(wq >> 1) * SBO_B + (uint32_t)(u & 7) * 16 + (uint32_t)(wq & 1) * 8;
+    float h[WPT];
+#pragma unroll
+    for (int w = 0; w < WPT; ++w) h[w] = 0.f;
+    // byte offset of (unit u, window 0) inside one B buffer (live windows are B columns 0..NW-1)
+    const uint32_t hoff = (uint32_t)(u >> 3) * LBO_B + (uint32_t)(u & 7) * 16;
     const uint32_t sB_addr = tc::smem_u32(sB), hbar_addr = tc::smem_u32(h_bar);
     const size_t gi_step = (size_t)G * 16, gt_step = (size_t)4 * H * 16;
-    const float* gi_p = (P.gi && valid) ? P.gi + ((size_t)tile * n * G + u) * 16 + wb : nullptr;
-    float* gt_p = (P.gates && valid) ? P.gates + ((size_t)tile * n * 4 * H + u) * 16 + wb : nullptr;
+    const float* gi_p = (P.gi && valid) ? P.gi + ((size_t)tile * n * G + u) * 16 + wo + wb : nullptr;
+    float* gt_p = (P.gates && valid) ? P.gates + ((size_t)tile * n * 4 * H + u) * 16 + wo + wb : nullptr;
     float* out_p = (P.out && valid) ? P.out + ((size_t)(b0 + wb) * n) * H + u : nullptr;
-    const int nvalid_w = max(0, min(4, P.B - (b0 + wb)));
+    const int nvalid_w = max(0, min(WPT, P.B - (b0 + wb)));
     const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
 
     // input-side pre-activations of step `tt` (independent of the recurrence): software-pipelined one step ahead
-    float gr[4], gz[4], gn[4];
+    float gr[WPT], gz[WPT], gn[WPT];
     auto load_inputs = [&](int tt) {
       if (P.gi) {
         if (valid) {
-          const float4* p = reinterpret_cast<const float4*>(gi_p + (size_t)tt * gi_step);
-          float4 a = __ldg(p), c = __ldg(p + (size_t)H * 4), e = __ldg(p + (size_t)2 * H * 4);
-          gr[0] = a.x; gr[1] = a.y; gr[2] = a.z; gr[3] = a.w;
-          gz[0] = c.x; gz[1] = c.y; gz[2] = c.z; gz[3] = c.w;
-          gn[0] = e.x; gn[1] = e.y; gn[2] = e.z; gn[3] = e.w;
+          const float* p = gi_p + (size_t)tt * gi_step;
+          ldg_w<WPT>(p, gr); ldg_w<WPT>(p + (size_t)H * 16, gz); ldg_w<WPT>(p + (size_t)2 * H * 16, gn);
         } else {
 #pragma unroll
-          for (int w = 0; w < 4; ++w) { gr[w] = 0.f; gz[w] = 0.f; gn[w] = 0.f; }
+          for (int w = 0; w < WPT; ++w) { gr[w] = 0.f; gz[w] = 0.f; gn[w] = 0.f; }
         }
       } else {
         const int m0 = (int)(((long long)tt * P.Hs) / n);
 #pragma unroll
-        for (int w = 0; w < 4; ++w) { gr[w] = bir; gz[w] = biz; gn[w] = bin; }
+        for (int w = 0; w < WPT; ++w) { gr[w] = bir; gz[w] = biz; gn[w] = bin; }
         if (valid)
-          for (int j = 0; j < P.J; ++j) {
-            int m = m0 + j;
-            if (m >= P.Hs) break;
-            const float* sp = P.S + ((size_t)tt * P.J + j) * G + u;
-            float sr = __ldg(sp), sz = __ldg(sp + H), sn = __ldg(sp + 2 * H);
+          for (int j = 0; j < P.J; j += 2) {
+            // two segments per trip, all six weight loads issued before the first use (one L2 round trip for J <= 2)
+            const int ma = m0 + j;
+            if (ma >= P.Hs) break;
+            const bool vb = (j + 1 < P.J) && (ma + 1 < P.Hs);
+            const int mb = vb ? ma + 1 : ma;
+            const float* spa = P.S + ((size_t)tt * P.J + j) * G + u;
+            const float* spb = vb ? spa + G : spa;
+            const float sra = __ldg(spa), sza = __ldg(spa + H), sna = __ldg(spa + 2 * H);
+            float srb = __ldg(spb), szb = __ldg(spb + H), snb = __ldg(spb + 2 * H);
+            if (!vb) { srb = 0.f; szb = 0.f; snb = 0.f; }
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              float hv = sHs[(wb + w) * P.Hs + m];
-              gr[w] = fmaf(hv, sr, gr[w]); gz[w] = fmaf(hv, sz, gz[w]); gn[w] = fmaf(hv, sn, gn[w]);
+            for (int w = 0; w < WPT; ++w) {
+              const float ha = sHs[(wb + w) * P.Hs + ma], hb = sHs[(wb + w) * P.Hs + mb];
+              gr[w] = fmaf(hb, srb, fmaf(ha, sra, gr[w]));
+              gz[w] = fmaf(hb, szb, fmaf(ha, sza, gz[w]));
+              gn[w] = fmaf(hb, snb, fmaf(ha, sna, gn[w]));
             }
           }
       }
@@ -260,24 +332,32 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
         tc::mbar_wait(acc_bar, t & 1);
         tc::tc_fence_after();
         e2 = clock64();
-        float v[16];
-        tc::tmem_ld16(tlane, v);
-        tc::tmem_ld_wait();
         float4* dst = reinterpret_cast<float4*>(sG + (size_t)(warp * 32 + lane) * SG_LD);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);   dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-        dst[2] = make_float4(v[8], v[9], v[10], v[11]); dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+        if (WPT == 4) {
+          float v[16];
+          tc::tmem_ld16(tlane, v);
+          tc::tmem_ld_wait();
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);   dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          dst[2] = make_float4(v[8], v[9], v[10], v[11]); dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+        } else {
+          float v[8];
+          tc::tmem_ld8(tlane, v);
+          tc::tmem_ld_wait();
+          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+          if (WPT == 2) dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
         tc::tc_fence_before();
       }
       named_bar_sync(1, EPI_THREADS);
       long long e3 = clock64(), e4 = e3;
-      float rr[4], zz[4], nv[4], hv_[4];
+      float rr[WPT], zz[WPT], nv[WPT], hv_[WPT];
       if (valid) {
-        const float4 ar = *reinterpret_cast<const float4*>(sG + (size_t)i * SG_LD + wb);
-        const float4 az = *reinterpret_cast<const float4*>(sG + (size_t)(Uc + i) * SG_LD + wb);
-        const float4 an = *reinterpret_cast<const float4*>(sG + (size_t)(2 * Uc + i) * SG_LD + wb);
-        const float arr[4] = {ar.x, ar.y, ar.z, ar.w}, azz[4] = {az.x, az.y, az.z, az.w}, ann[4] = {an.x, an.y, an.z, an.w};
+        float arr[WPT], azz[WPT], ann[WPT];
+        ld_w<WPT>(sG + (size_t)i * SG_LD + wb, arr);
+        ld_w<WPT>(sG + (size_t)(Uc + i) * SG_LD + wb, azz);
+        ld_w<WPT>(sG + (size_t)(2 * Uc + i) * SG_LD + wb, ann);
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < WPT; ++w) {
           float r = sigm(gr[w] + arr[w] + bhr);
           float z = sigm(gz[w] + azz[w] + bhz);
           float hn = ann[w] + bhn;
@@ -287,31 +367,22 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
         }
       }
       e4 = clock64();
-      if (t + 1 < n) {
-        // hand h_t to every CTA of the cluster with asynchronous stores that complete tx-bytes on the destination's
-        // mbarrier (no fences / release-arrives on the producer side).  Lane pairs (wq, wq^1) merge their 4+4
-        // windows into one 16-byte store to halve the number of barrier updates.
-        const uint32_t p0 = pack_h2(h[0], h[1]), p1 = pack_h2(h[2], h[3]);
-        const uint32_t o0 = __shfl_xor_sync(0xffffffffu, p0, 1), o1 = __shfl_xor_sync(0xffffffffu, p1, 1);
-        if (valid && !(wq & 1)) {
-          const uint32_t dst = sB_addr + (uint32_t)(((t + 1) & 1) * KC * LBO_B) + hoff;
-          for (int r = 0; r < CS; ++r) st_async_v4(mapa(dst, (uint32_t)r), p0, p1, o0, o1, mapa(hbar_addr, (uint32_t)r));
-        }
-      }
+      // hand h_t to every CTA of the cluster with asynchronous stores that complete tx-bytes on the destination's
+      // mbarrier (no fences / release-arrives on the producer side)
+      if (t + 1 < n)
+        send_quad<WPT>(h, 1.f, valid, wq, sB_addr + (uint32_t)(((t + 1) & 1) * KC * LBO_B), hoff, hbar_addr, CS);
       long long e5 = clock64();
       // everything below overlaps with the next step's MMAs
       if (valid) {
         if (out_p) {
 #pragma unroll
-          for (int w = 0; w < 4; ++w)
+          for (int w = 0; w < WPT; ++w)
             if (w < nvalid_w) out_p[((size_t)w * n + t) * H] = h[w];
         }
         if (gt_p) {
-          float4* gq = reinterpret_cast<float4*>(gt_p + (size_t)t * gt_step);
-          gq[0] = make_float4(rr[0], rr[1], rr[2], rr[3]);
-          gq[(size_t)H * 4] = make_float4(zz[0], zz[1], zz[2], zz[3]);
-          gq[(size_t)2 * H * 4] = make_float4(nv[0], nv[1], nv[2], nv[3]);
-          gq[(size_t)3 * H * 4] = make_float4(hv_[0], hv_[1], hv_[2], hv_[3]);
+          float* gq = gt_p + (size_t)t * gt_step;
+          st_w<WPT>(gq, rr); st_w<WPT>(gq + (size_t)H * 16, zz); st_w<WPT>(gq + (size_t)2 * H * 16, nv);
+          st_w<WPT>(gq + (size_t)3 * H * 16, hv_);
         }
       }
       if (t + 1 < n) load_inputs(t + 1);
@@ -326,7 +397,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams P
     }
     if (valid && P.h_last) {
 #pragma unroll
-      for (int w = 0; w < 4; ++w)
+      for (int w = 0; w < WPT; ++w)
         if (w < nvalid_w) P.h_last[(size_t)(b0 + wb + w) * H + u] = h[w];
     }
   }
@@ -353,7 +424,9 @@ static size_t cl_bwd_smem(int H) {
   return (size_t)KC * 64 * 16 + 2 * (size_t)KC * LBO_B + (size_t)64 * SG_LD * 4 + 128;
 }
 
-__global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P) {
+template <int WPT>
+__global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_bwd_kernel(ClBwdParams P) {
+  constexpr int NW = 4 * WPT, SPLIT = NB / NW;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int H = P.H, G = 3 * H, n = P.n, CS = P.CS, Uc = P.Uc;
   const int Hp = CS * Uc;                                   // padded gate width: k = gate*Hp + unit
@@ -368,7 +441,8 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rank = (int)cluster_ctarank();
-  const int tile = blockIdx.x / CS, b0 = tile * NB;
+  const int cid = blockIdx.x / CS;
+  const int tile = cid / SPLIT, wo = (cid % SPLIT) * NW, b0 = tile * NB + wo;
   const int u0 = rank * Uc, nu = max(0, min(Uc, H - u0));
 
   for (int idx = tid; idx < 64 * Kp; idx += CL_THREADS) {
@@ -397,7 +471,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
     const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
     const uint32_t ainc = (uint32_t)(2 * lboA) >> 4, binc = (uint32_t)(2 * LBO_B) >> 4;
     const int nkc = Kp / 16;
-    const uint32_t tx_bytes = (uint32_t)3 * H * NB * 2;      // all CTAs' (dpr, dpz, dgh_n) slices for 16 windows
+    const uint32_t tx_bytes = (uint32_t)3 * H * NW * 2;      // all CTAs' (dpr, dpz, dgh_n) slices for NW windows
     if (n > 1 && tc::elect_one()) mbar_arrive_expect_tx(h_bar, tx_bytes);
     __syncwarp();
     for (int it = 0; it < n - 1; ++it) {
@@ -417,39 +491,37 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
       __syncwarp();
     }
   } else {
-    const int i = tid >> 2, wq = tid & 3, wb = 4 * wq;
+    const int i = tid >> 2, wq = tid & 3, wb = WPT * wq;
     const bool valid = i < nu;
     const int u = u0 + i;
     const float gmax = __uint_as_float(*P.gmax_bits);
     const float scale = gmax > 0.f ? exp2f(floorf(log2f(64.f / gmax))) : 1.f;
     const float inv_scale = 1.f / scale;
-    float dhz[4] = {0.f, 0.f, 0.f, 0.f};
-    const uint32_t woff = (uint32_t)(wq >> 1) * SBO_B + (uint32_t)(wq & 1) * 8;
-    const uint32_t off0 = (uint32_t)(u >> 3) * LBO_B + (uint32_t)(u & 7) * 16 + woff;
-    const uint32_t off1 = (uint32_t)((Hp + u) >> 3) * LBO_B + (uint32_t)((Hp + u) & 7) * 16 + woff;
-    const uint32_t off2 = (uint32_t)((2 * Hp + u) >> 3) * LBO_B + (uint32_t)((2 * Hp + u) & 7) * 16 + woff;
+    float dhz[WPT];
+#pragma unroll
+    for (int w = 0; w < WPT; ++w) dhz[w] = 0.f;
+    const uint32_t off0 = (uint32_t)(u >> 3) * LBO_B + (uint32_t)(u & 7) * 16;
+    const uint32_t off1 = (uint32_t)((Hp + u) >> 3) * LBO_B + (uint32_t)((Hp + u) & 7) * 16;
+    const uint32_t off2 = (uint32_t)((2 * Hp + u) >> 3) * LBO_B + (uint32_t)((2 * Hp + u) & 7) * 16;
     const uint32_t sB_addr = tc::smem_u32(sB), hbar_addr = tc::smem_u32(h_bar);
     const size_t gt_step = (size_t)4 * H * 16, gi_step = (size_t)G * 16, gn_step = (size_t)H * 16;
-    const float* gt_p = valid ? P.gates + ((size_t)tile * n * 4 * H + u) * 16 + wb : nullptr;
-    float* dgi_p = valid ? P.dgi + ((size_t)tile * n * G + u) * 16 + wb : nullptr;
-    float* dgn_p = valid ? P.dghn + ((size_t)tile * n * H + u) * 16 + wb : nullptr;
-    const int nvalid_w = max(0, min(4, P.B - (b0 + wb)));
+    const float* gt_p = valid ? P.gates + ((size_t)tile * n * 4 * H + u) * 16 + wo + wb : nullptr;
+    float* dgi_p = valid ? P.dgi + ((size_t)tile * n * G + u) * 16 + wo + wb : nullptr;
+    float* dgn_p = valid ? P.dghn + ((size_t)tile * n * H + u) * 16 + wo + wb : nullptr;
+    const int nvalid_w = max(0, min(WPT, P.B - (b0 + wb)));
     const size_t row0 = (size_t)(b0 + wb) * n;
     // M = 64 accumulator: row i lives in TMEM lane 32*(i/16) + i%16  -> warp q drains rows 16q .. 16q+15
     const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
 
     // everything of step `tt` that does not depend on the recurrence (software-pipelined one step ahead)
-    float dh[4], hp[4], r[4], z[4], nn[4], hn[4];
+    float dh[WPT], hp[WPT], r[WPT], z[WPT], nn[WPT], hn[WPT];
     auto load_step = [&](int tt) {
       if (valid) {
-        const float4* gq = reinterpret_cast<const float4*>(gt_p + (size_t)tt * gt_step);
-        float4 a = __ldg(gq), c = __ldg(gq + (size_t)H * 4), e = __ldg(gq + (size_t)2 * H * 4), f = __ldg(gq + (size_t)3 * H * 4);
-        r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
-        z[0] = c.x; z[1] = c.y; z[2] = c.z; z[3] = c.w;
-        nn[0] = e.x; nn[1] = e.y; nn[2] = e.z; nn[3] = e.w;
-        hn[0] = f.x; hn[1] = f.y; hn[2] = f.z; hn[3] = f.w;
+        const float* gq = gt_p + (size_t)tt * gt_step;
+        ldg_w<WPT>(gq, r); ldg_w<WPT>(gq + (size_t)H * 16, z); ldg_w<WPT>(gq + (size_t)2 * H * 16, nn);
+        ldg_w<WPT>(gq + (size_t)3 * H * 16, hn);
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < WPT; ++w) {
           float v = 0.f, p = 0.f;
           if (w < nvalid_w) {
             size_t o = (row0 + (size_t)w * n + tt) * H + u;
@@ -461,7 +533,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
         }
       } else {
 #pragma unroll
-        for (int w = 0; w < 4; ++w) { dh[w] = 0.f; hp[w] = 0.f; r[w] = 0.f; z[w] = 0.f; nn[w] = 0.f; hn[w] = 0.f; }
+        for (int w = 0; w < WPT; ++w) { dh[w] = 0.f; hp[w] = 0.f; r[w] = 0.f; z[w] = 0.f; nn[w] = 0.f; hn[w] = 0.f; }
       }
     };
     load_step(n - 1);
@@ -472,64 +544,57 @@ __global__ void __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams P
         if (warp < 4) {
           tc::mbar_wait(acc_bar, (it - 1) & 1);
           tc::tc_fence_after();
-          float v[16];
-          tc::tmem_ld16(tlane, v);
-          tc::tmem_ld_wait();
-          if (lane < 16) {
-            float4* dst = reinterpret_cast<float4*>(sG + (size_t)(warp * 16 + lane) * SG_LD);
-            dst[0] = make_float4(v[0], v[1], v[2], v[3]);   dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-            dst[2] = make_float4(v[8], v[9], v[10], v[11]); dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+          float4* dst = reinterpret_cast<float4*>(sG + (size_t)(warp * 16 + (lane & 15)) * SG_LD);
+          if (WPT == 4) {
+            float v[16];
+            tc::tmem_ld16(tlane, v);
+            tc::tmem_ld_wait();
+            if (lane < 16) {
+              dst[0] = make_float4(v[0], v[1], v[2], v[3]);   dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+              dst[2] = make_float4(v[8], v[9], v[10], v[11]); dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+            }
+          } else {
+            float v[8];
+            tc::tmem_ld8(tlane, v);
+            tc::tmem_ld_wait();
+            if (lane < 16) {
+              dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+              if (WPT == 2) dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
           }
           tc::tc_fence_before();
         }
         named_bar_sync(1, EPI_THREADS);
         if (valid) {
-          const float4 acc = *reinterpret_cast<const float4*>(sG + (size_t)i * SG_LD + wb);
-          dh[0] += dhz[0] + acc.x * inv_scale; dh[1] += dhz[1] + acc.y * inv_scale;
-          dh[2] += dhz[2] + acc.z * inv_scale; dh[3] += dhz[3] + acc.w * inv_scale;
+          float acc[WPT];
+          ld_w<WPT>(sG + (size_t)i * SG_LD + wb, acc);
+#pragma unroll
+          for (int w = 0; w < WPT; ++w) dh[w] += dhz[w] + acc[w] * inv_scale;
         }
       }
-      float dpr[4], dpz[4], dpn[4], dgn[4];
-      if (valid) {
+      float dpr[WPT], dpz[WPT], dpn[WPT], dgn[WPT];
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
-          float d = dh[w];
-          float dn = d * (1.f - z[w]);
-          float dz = d * (hp[w] - nn[w]);
-          dpn[w] = dn * (1.f - nn[w] * nn[w]);
-          dpz[w] = dz * z[w] * (1.f - z[w]);
-          dpr[w] = dpn[w] * hn[w] * r[w] * (1.f - r[w]);
-          dgn[w] = dpn[w] * r[w];
-          dhz[w] = d * z[w];
-        }
+      for (int w = 0; w < WPT; ++w) {
+        float d = dh[w];
+        float dn = d * (1.f - z[w]);
+        float dz = d * (hp[w] - nn[w]);
+        dpn[w] = dn * (1.f - nn[w] * nn[w]);
+        dpz[w] = dz * z[w] * (1.f - z[w]);
+        dpr[w] = dpn[w] * hn[w] * r[w] * (1.f - r[w]);
+        dgn[w] = dpn[w] * r[w];
+        dhz[w] = d * z[w];
       }
       if (t > 0) {
-        uint32_t a0 = 0, a1 = 0, c0 = 0, c1 = 0, e0 = 0, e1 = 0;
-        if (valid) {
-          a0 = pack_h2(sat_h(dpr[0] * scale), sat_h(dpr[1] * scale)); a1 = pack_h2(sat_h(dpr[2] * scale), sat_h(dpr[3] * scale));
-          c0 = pack_h2(sat_h(dpz[0] * scale), sat_h(dpz[1] * scale)); c1 = pack_h2(sat_h(dpz[2] * scale), sat_h(dpz[3] * scale));
-          e0 = pack_h2(sat_h(dgn[0] * scale), sat_h(dgn[1] * scale)); e1 = pack_h2(sat_h(dgn[2] * scale), sat_h(dgn[3] * scale));
-        }
-        const uint32_t a2 = __shfl_xor_sync(0xffffffffu, a0, 1), a3 = __shfl_xor_sync(0xffffffffu, a1, 1);
-        const uint32_t c2 = __shfl_xor_sync(0xffffffffu, c0, 1), c3 = __shfl_xor_sync(0xffffffffu, c1, 1);
-        const uint32_t e2 = __shfl_xor_sync(0xffffffffu, e0, 1), e3 = __shfl_xor_sync(0xffffffffu, e1, 1);
-        if (valid && !(wq & 1)) {
-          const uint32_t buf = sB_addr + (uint32_t)((it & 1) * KC * LBO_B);
-          for (int rr = 0; rr < CS; ++rr) {
-            const uint32_t mb = mapa(hbar_addr, (uint32_t)rr);
-            st_async_v4(mapa(buf + off0, (uint32_t)rr), a0, a1, a2, a3, mb);
-            st_async_v4(mapa(buf + off1, (uint32_t)rr), c0, c1, c2, c3, mb);
-            st_async_v4(mapa(buf + off2, (uint32_t)rr), e0, e1, e2, e3, mb);
-          }
-        }
+        const uint32_t buf = sB_addr + (uint32_t)((it & 1) * KC * LBO_B);
+        send_quad<WPT>(dpr, scale, valid, wq, buf, off0, hbar_addr, CS);
+        send_quad<WPT>(dpz, scale, valid, wq, buf, off1, hbar_addr, CS);
+        send_quad<WPT>(dgn, scale, valid, wq, buf, off2, hbar_addr, CS);
       }
       if (valid) {
         // fp32 results for the weight-gradient GEMMs, after the hand-off
-        float4* q4 = reinterpret_cast<float4*>(dgi_p + (size_t)t * gi_step);
-        q4[0] = make_float4(dpr[0], dpr[1], dpr[2], dpr[3]);
-        q4[(size_t)H * 4] = make_float4(dpz[0], dpz[1], dpz[2], dpz[3]);
-        q4[(size_t)2 * H * 4] = make_float4(dpn[0], dpn[1], dpn[2], dpn[3]);
-        *reinterpret_cast<float4*>(dgn_p + (size_t)t * gn_step) = make_float4(dgn[0], dgn[1], dgn[2], dgn[3]);
+        float* q = dgi_p + (size_t)t * gi_step;
+        st_w<WPT>(q, dpr); st_w<WPT>(q + (size_t)H * 16, dpz); st_w<WPT>(q + (size_t)2 * H * 16, dpn);
+        st_w<WPT>(dgn_p + (size_t)t * gn_step, dgn);
       }
       if (t > 0) load_step(t - 1);
     }
@@ -569,9 +634,24 @@ static int launch_cluster(Kern kern, const Params& P, int nblocks, int cs, size_
 }
 
 static long long* g_dbg = nullptr;
+static int g_split = 0;               // 0 = auto, else clusters per 16-window tile (1, 2 or 4)
+
+// clusters per 16-window tile: split the tile while the grid still fits ~2 CTAs per SM
+static int pick_split(int B, int CS) {
+  if (g_split) return g_split;
+  const int tiles = cdiv(B, NB);
+  int split = 1;
+  while (split < 2 && tiles * CS * split * 2 <= 148) split *= 2;   // split 4 (two CTAs per SM) is opt-in
+  return split;
+}
 }  // namespace
 
 extern "C" void mtadgat_gru_debug_buffer(long long* dev_ptr) { g_dbg = dev_ptr; }
+extern "C" int mtadgat_set_gru_split(int split) {
+  MG_CHECK_ARG(split == 0 || split == 1 || split == 2 || split == 4, "set_gru_split: 0 (auto), 1, 2 or 4 clusters per 16-window tile");
+  g_split = split;
+  return MTADGAT_OK;
+}
 
 int mtadgat_gru_cl_supported(int H, int Hs_rep) {
   ClGeom g;
@@ -588,7 +668,11 @@ int mtadgat_gru_cl_fwd_launch(const float* gi_t, const float* S, const float* hs
   P.gi = gi_t; P.S = S; P.hsrc = hsrc; P.b_ih = b_ih; P.J = J; P.Hs = Hs; P.w_hh = w_hh; P.b_hh = b_hh;
   P.out = out; P.h_last = h_last; P.gates = gates_t; P.B = B; P.n = n; P.H = H; P.CS = g.CS; P.Uc = g.Uc;
   P.dbg = g_dbg;
-  return launch_cluster(gru_cl_fwd_kernel, P, cdiv(B, NB) * g.CS, g.CS, cl_fwd_smem(H, gi_t ? 0 : Hs), s);
+  const int split = pick_split(B, g.CS), nblocks = cdiv(B, NB) * split * g.CS;
+  const size_t smem = cl_fwd_smem(H, gi_t ? 0 : Hs);
+  if (split == 4) return launch_cluster(gru_cl_fwd_kernel<1>, P, nblocks, g.CS, smem, s);
+  if (split == 2) return launch_cluster(gru_cl_fwd_kernel<2>, P, nblocks, g.CS, smem, s);
+  return launch_cluster(gru_cl_fwd_kernel<4>, P, nblocks, g.CS, smem, s);
 }
 
 int mtadgat_gru_cl_bwd_launch(const float* gates_t, const float* out, const float* w_hh, const float* dout,
@@ -602,5 +686,9 @@ int mtadgat_gru_cl_bwd_launch(const float* gates_t, const float* out, const floa
   ClBwdParams P;
   P.gates = gates_t; P.out = out; P.w_hh = w_hh; P.dout = dout; P.dh_last = dh_last; P.gmax_bits = gmax_bits;
   P.dgi = dgi_t; P.dghn = dghn_t; P.B = B; P.n = n; P.H = H; P.CS = g.CS; P.Uc = g.Uc;
-  return launch_cluster(gru_cl_bwd_kernel, P, cdiv(B, NB) * g.CS, g.CS, cl_bwd_smem(H), s);
+  const int split = pick_split(B, g.CS), nblocks = cdiv(B, NB) * split * g.CS;
+  const size_t smem = cl_bwd_smem(H);
+  if (split == 4) return launch_cluster(gru_cl_bwd_kernel<1>, P, nblocks, g.CS, smem, s);
+  if (split == 2) return launch_cluster(gru_cl_bwd_kernel<2>, P, nblocks, g.CS, smem, s);
+  return launch_cluster(gru_cl_bwd_kernel<4>, P, nblocks, g.CS, smem, s);
 }

@@ -1,0 +1,234 @@
+// Packed-operand tensor-core GEMM for sm_100a (the default GEMM of the MTAD-GAT path).
+//
+// tc_gemm.cuh gathers its operand tiles inside the GEMM main loop: ~800 instructions per warp and k-tile of address
+// arithmetic on 8 warps per SM, i.e. a latency-bound instruction stream (ncu: 0.1 issued warps per scheduler) and
+// 40-120 us for GEMMs that hold a few GFLOP.  Here the two concerns are split:
+//   1. pack_kernel -- an elementwise, full-occupancy kernel that evaluates the operand functors ONCE per element
+//      (same OpA / OpB line/load8 protocol), splits every fp32 value into bf16 hi / lo terms and writes them to a
+//      workspace in TILE-CANONICAL order: [line tile][k tile][hi|lo][k group of 8][row][8 x bf16], i.e. exactly the
+//      K-major no-swizzle shared-memory image one MMA k-tile needs (16 KB per 128-row operand);
+//   2. gemm2_kernel -- per k-tile ONE bulk asynchronous copy (cp.async.bulk global -> shared, completion on an
+//      mbarrier) per operand by a producer lane, tcgen05.mma kind::f16 bf16x3 issued by a second warp straight from
+//      the landed tiles (3-stage ring, stage release through tcgen05.commit), fp32 accumulator in TMEM, epilogue
+//      through tcgen05.ld and the store functor.  No CUDA-core work in the main loop.
+// The workspace is a grow-only device buffer per stream owned by the library (mtadgat_workspace); it must exist
+// before a stream is captured into a CUDA graph (one eager call, or mtadgat_workspace_reserve).
+#pragma once
+#include "tc_gemm.cuh"
+
+uint8_t* mtadgat_workspace(cudaStream_t s, size_t bytes);   // api.cu; nullptr + error message when it cannot grow
+void mtadgat_set_pending_error(int rc);
+
+namespace tcg2 {
+
+constexpr int BM = 128, BK = 32, KG = BK / 8, NTHREADS = 256, STAGES = 3;
+template <int R> struct Tile { static constexpr int HALF = KG * R * 16, BYTES = 2 * HALF; };   // hi block, lo block
+
+// functors whose value does not depend on the batch index z are packed once (specialise to true)
+template <class F> struct BatchInvariant { static constexpr bool value = false; };
+
+template <class Op, class F, int R>
+__device__ __forceinline__ void pack_row(const F& f, int z, int L, int K, int ltile, int ktile, int row, uint8_t* tile) {
+  const int l = ltile * R + row;
+  uint8_t* hi = tile;
+  uint8_t* lo = tile + Tile<R>::HALF;
+  if (l < L) {
+    const typename Op::Ctx ctx = Op::line(f, z, l);
+#pragma unroll
+    for (int g = 0; g < KG; ++g) {
+      float v[8];
+      Op::load8(f, ctx, z, ktile * BK + g * 8, K, v);
+      tcg::store_split8(hi, lo, (uint32_t)(g * R + row) * 16, v);
+    }
+  } else {
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int g = 0; g < KG; ++g) {
+      *reinterpret_cast<uint4*>(hi + (size_t)(g * R + row) * 16) = zero;
+      *reinterpret_cast<uint4*>(lo + (size_t)(g * R + row) * 16) = zero;
+    }
+  }
+}
+
+// one thread per (z, line tile, k tile, row): 32 consecutive K of one operand line -> 4 hi + 4 lo 16-byte groups.
+// Threads [0, nA) pack A, the rest pack B (both counts are multiples of 32: warps never straddle).
+template <class AL, class BL, int BN>
+__global__ void __launch_bounds__(256) pack_kernel(AL A, BL Bm, int M, int N, int K, int KT, int MT, int NT, int nzA,
+                                                   int nzB, uint8_t* __restrict__ Ap, uint8_t* __restrict__ Bp) {
+  long long g = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long nA = (long long)nzA * MT * KT * BM, nB = (long long)nzB * NT * KT * BN;
+  if (g < nA) {
+    const int row = (int)(g % BM);
+    long long tile = g / BM;
+    const int ktile = (int)(tile % KT);
+    const long long t2 = tile / KT;
+    pack_row<tcg::OpA<AL>, AL, BM>(A, (int)(t2 / MT), M, K, (int)(t2 % MT), ktile, row, Ap + tile * Tile<BM>::BYTES);
+  } else if (g - nA < nB) {
+    g -= nA;
+    const int row = (int)(g % BN);
+    long long tile = g / BN;
+    const int ktile = (int)(tile % KT);
+    const long long t2 = tile / KT;
+    pack_row<tcg::OpB<BL>, BL, BN>(Bm, (int)(t2 / NT), N, K, (int)(t2 % NT), ktile, row, Bp + tile * Tile<BN>::BYTES);
+  }
+}
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+template <int BN> struct Smem2 {
+  static constexpr int STAGE = Tile<BM>::BYTES + Tile<BN>::BYTES;
+  static constexpr int TOTAL = STAGES * STAGE + 128;
+};
+
+// C(z,m,n) = sum_k A(z,m,k) B(z,k,n) from packed operands; batch / split-K semantics as gemm_kernel (split-K over
+// whole k-tiles: blockIdx.z owns k-tiles [z*kt_len, (z+1)*kt_len))
+template <class CS, int BN>
+__global__ void __launch_bounds__(NTHREADS) gemm2_kernel(const uint8_t* __restrict__ Ap, const uint8_t* __restrict__ Bp,
+                                                         int M, int N, int KT, int kt_len, int splitk, int MT, int NT,
+                                                         int zA, int zB, CS C) {
+  using S = Smem2<BN>;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * S::STAGE);   // [STAGES] tile landed
+  uint64_t* empty = full + STAGES;                                              // [STAGES] MMAs that read it are done
+  uint64_t* accb = empty + STAGES;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(accb + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int z = splitk ? 0 : blockIdx.z;
+  const int kt0 = splitk ? blockIdx.z * kt_len : 0;
+  const int kt1 = splitk ? min(KT, kt0 + kt_len) : KT;
+  const int nkt = kt1 - kt0;
+  const int mt = blockIdx.y, nt = blockIdx.x;
+  const int m0 = mt * BM, n0 = nt * BN;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(full + s, 1); tc::mbar_init(empty + s, 1); }
+    tc::mbar_init(accb, 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc(slot, BN);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = *slot;
+  const uint32_t sbase = tc::smem_u32(smem_raw);
+
+  if (warp == 0) {
+    // ---- producer: one lane streams the packed tiles of this CTA's (m tile, n tile) ----
+    if (lane == 0 && nkt > 0) {
+      const uint8_t* a_src = Ap + ((size_t)((zA ? z : 0) * MT + mt) * KT + kt0) * Tile<BM>::BYTES;
+      const uint8_t* b_src = Bp + ((size_t)((zB ? z : 0) * NT + nt) * KT + kt0) * Tile<BN>::BYTES;
+      for (int i = 0; i < nkt; ++i) {
+        const int s = i % STAGES;
+        if (i >= STAGES) tc::mbar_wait(empty + s, ((i / STAGES) - 1) & 1);
+        arrive_expect_tx(full + s, (uint32_t)S::STAGE);
+        bulk_g2s(sbase + (uint32_t)(s * S::STAGE), a_src + (size_t)i * Tile<BM>::BYTES, Tile<BM>::BYTES, full + s);
+        bulk_g2s(sbase + (uint32_t)(s * S::STAGE) + Tile<BM>::BYTES, b_src + (size_t)i * Tile<BN>::BYTES, Tile<BN>::BYTES,
+                 full + s);
+      }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: whole warp runs the uniform loop, one elected lane issues ----
+    const uint32_t idesc = tc::make_idesc_f16(BM, BN, /*bf16=*/1);
+    for (int i = 0; i < nkt; ++i) {
+      const int s = i % STAGES;
+      tc::mbar_wait(full + s, (i / STAGES) & 1);
+      tc::tc_fence_after();
+      const uint32_t a0 = sbase + (uint32_t)(s * S::STAGE), b0 = a0 + Tile<BM>::BYTES;
+#pragma unroll
+      for (int j = 0; j < BK / 16; ++j) {
+        const uint32_t ao = (uint32_t)(2 * j) * BM * 16, bo = (uint32_t)(2 * j) * BN * 16;
+        const uint64_t dAh = tc::make_smem_desc(a0 + ao, BM * 16, 128);
+        const uint64_t dAl = tc::make_smem_desc(a0 + Tile<BM>::HALF + ao, BM * 16, 128);
+        const uint64_t dBh = tc::make_smem_desc(b0 + bo, BN * 16, 128);
+        const uint64_t dBl = tc::make_smem_desc(b0 + Tile<BN>::HALF + bo, BN * 16, 128);
+        if (tc::elect_one()) {
+          tc::mma_f16_ss(tbase, dAl, dBh, idesc, (i > 0 || j > 0) ? 1u : 0u);   // small terms first
+          tc::mma_f16_ss(tbase, dAh, dBl, idesc, 1u);
+          tc::mma_f16_ss(tbase, dAh, dBh, idesc, 1u);
+        }
+      }
+      if (tc::elect_one()) {
+        tc::mma_commit(empty + s);
+        if (i == nkt - 1) tc::mma_commit(accb);
+      }
+      __syncwarp();
+    }
+  }
+  __syncwarp();                       // warp 0: the producer lane rejoins its warp
+  // ---- epilogue: warp w reads TMEM lanes 32*(w&3).., columns [ (w>>2)*BN/2, +BN/2 ) ----
+  if (nkt > 0) {
+    tc::mbar_wait(accb, 0);
+    tc::tc_fence_after();
+    const int q = warp & 3, half = warp >> 2;
+    const int gm = m0 + q * 32 + lane;
+#pragma unroll 1
+    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
+      if (n0 + c0 >= N) break;
+      float v[16];
+      tc::tmem_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      tc::tmem_ld_wait();
+      if (gm < M) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          int gn = n0 + c0 + i;
+          if (gn < N) C(z, gm, gn, v[i], splitk != 0);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tbase, BN);
+}
+
+template <class AL, class BL, class CS, int BN>
+static inline int run(int batch, int M, int N, int K, int splits_wanted, bool splitk, AL A, BL Bm, CS C, cudaStream_t s) {
+  const int KT = cdiv(K, BK), MT = cdiv(M, BM), NT = cdiv(N, BN);
+  const int nzA = (!splitk && !BatchInvariant<AL>::value) ? batch : 1;
+  const int nzB = (!splitk && !BatchInvariant<BL>::value) ? batch : 1;
+  const size_t a_bytes = (size_t)nzA * MT * KT * Tile<BM>::BYTES, b_bytes = (size_t)nzB * NT * KT * Tile<BN>::BYTES;
+  uint8_t* ws = mtadgat_workspace(s, a_bytes + b_bytes);
+  if (!ws) { mtadgat_set_pending_error(MTADGAT_ERR_CUDA); return MTADGAT_ERR_CUDA; }
+  uint8_t* Ap = ws; uint8_t* Bp = ws + a_bytes;
+  const long long nthreads = (long long)nzA * MT * KT * BM + (long long)nzB * NT * KT * BN;
+  pack_kernel<AL, BL, BN><<<cdiv(nthreads, 256), 256, 0, s>>>(A, Bm, M, N, K, KT, MT, NT, nzA, nzB, Ap, Bp);
+  MG_COUNT_LAUNCH();
+  constexpr int smem = Smem2<BN>::TOTAL;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(gemm2_kernel<CS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  int kt_len = KT, nz = batch;
+  if (splitk) {
+    int splits = max(1, min(KT, splits_wanted));
+    kt_len = cdiv(KT, splits);
+    nz = cdiv(KT, kt_len);
+  }
+  gemm2_kernel<CS, BN><<<dim3(NT, MT, nz), NTHREADS, smem, s>>>(Ap, Bp, M, N, KT, kt_len, splitk ? 1 : 0, MT, NT,
+                                                               nzA > 1 ? 1 : 0, nzB > 1 ? 1 : 0, C);
+  MG_COUNT_LAUNCH();
+  return MTADGAT_OK;
+}
+
+template <class AL, class BL, class CS>
+static inline int launch_batched(int batch, int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s) {
+  if (N <= 64) return run<AL, BL, CS, 64>(batch, M, N, K, 1, false, A, Bm, C, s);
+  return run<AL, BL, CS, 128>(batch, M, N, K, 1, false, A, Bm, C, s);
+}
+
+template <class AL, class BL, class CS>
+static inline int launch_splitk(int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s, int target_ctas) {
+  const int bn = N <= 64 ? 64 : 128;
+  const int tiles = cdiv(N, bn) * cdiv(M, BM);
+  const int splits = max(1, min(cdiv(K, 4 * BK), cdiv(target_ctas, tiles)));
+  if (bn == 64) return run<AL, BL, CS, 64>(1, M, N, K, splits, true, A, Bm, C, s);
+  return run<AL, BL, CS, 128>(1, M, N, K, splits, true, A, Bm, C, s);
+}
+
+}  // namespace tcg2

@@ -297,9 +297,15 @@ def set_gru_impl(name):
     check(lib.mtadgat_set_gru_impl({"fp32": 0, "tc": 1, "tc1": 2}[name]))
 
 
+def set_gru_split(split):
+    """Clusters per 16-window tile in the cluster recurrence: 0 = auto (default), 1, 2 or 4."""
+    check(lib.mtadgat_set_gru_split(int(split)))
+
+
 def set_gemm_impl(name):
-    """'tc' (default): tcgen05 bf16x3 GEMMs; 'fp32': SIMT fp32 GEMMs."""
-    check(lib.mtadgat_set_gemm_impl({"fp32": 0, "tc": 1}[name]))
+    """'tc' (default): tcgen05 bf16x3 GEMMs on packed operands; 'tc_gather': same arithmetic, operands gathered inside
+    the GEMM kernel; 'fp32': SIMT fp32 GEMMs."""
+    check(lib.mtadgat_set_gemm_impl({"fp32": 0, "tc": 1, "tc_gather": 2}[name]))
 
 
 def set_mode(name):

@@ -75,6 +75,45 @@ def stage_rooflines(model, B, peaks, dev):
     rp = list(model.recon_model.parameters())
     add("recon", lambda: model.recon_model(h_end), [h_end] + rp, (H + n * out_dim) * 4 * B,
         (2 * n * R * 3 * R + 2 * n * R * out_dim) * B, "tensor")
+    rows += recurrence_rooflines(B, n, H, model.gru.gru.weight_hh_l0.detach(), model.gru.gru.bias_hh_l0.detach(), peaks, dev, flush)
     model.train(was_training)
     del flush
+    return rows
+
+
+def recurrence_rooflines(B, n, H, w_hh, b_hh, peaks, dev, flush):
+    """The recurrence launches alone (mtadgat_gru_recurrence_fwd / _bwd = the persistent cluster kernels; the BPTT entry
+    also runs a 5 us absmax pre-pass) on synthetic window-tiled operands.  Algorithmic bytes: every operand read or
+    written once (fp32); FLOPs: the h_{t-1} W_hh^T products (2*3H*H per window and step, same for dh)."""
+    from ._lib import lib
+    Bp = (B + 15) // 16 * 16
+    st = torch.cuda.current_stream().cuda_stream
+    gi = torch.randn(Bp * n * 3 * H, device=dev) * 0.5
+    wt = torch.empty(3 * H * H, device=dev)
+    out = torch.empty(B, n, H, device=dev)
+    hl = torch.empty(B, H, device=dev)
+    gates = torch.empty(Bp * n * 4 * H, device=dev)
+    dout = torch.randn(B, n, H, device=dev) * 1e-3
+    dgi = torch.empty(Bp * n * 3 * H, device=dev)
+    dghn = torch.empty(Bp * n * H, device=dev)
+    gmax = torch.zeros(1, dtype=torch.int32, device=dev)
+    w_hh = w_hh.contiguous(); b_hh = b_hh.contiguous()
+    f = lambda: F.check(lib.mtadgat_gru_recurrence_fwd(gi.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), wt.data_ptr(),
+                                                      out.data_ptr(), hl.data_ptr(), gates.data_ptr(), B, n, H, st))
+    b = lambda: F.check(lib.mtadgat_gru_recurrence_bwd(gates.data_ptr(), out.data_ptr(), w_hh.data_ptr(), dout.data_ptr(),
+                                                      None, dgi.data_ptr(), dghn.data_ptr(), gmax.data_ptr(), B, n, H, st))
+    ms_f = _time(f, flush, reps=9)
+    ms_b = _time(b, flush, reps=9)
+    flops = 2.0 * 3 * H * H * n * B
+    by_f = 4.0 * n * (Bp * 3 * H + B * H + Bp * 4 * H)
+    by_b = 4.0 * n * (Bp * 4 * H + 2 * B * H + Bp * 4 * H + B * H)
+    rows = []
+    for name, ms, by in (("gru_recurrence_fwd_kernel", ms_f, by_f), ("gru_recurrence_bwd_kernel", ms_b, by_b)):
+        hb, tf = by / (ms * 1e-3) / 1e9, flops / (ms * 1e-3) / 1e12
+        fh, ft = hb / peaks["hbm_gbs"], tf / peaks["bf16_tflops"]
+        bound = "hbm" if fh >= ft else "tensor"
+        rows.append({"kernel": name, "ms": ms, "bound": bound, "achieved": hb if bound == "hbm" else tf,
+                     "peak": peaks["hbm_gbs"] if bound == "hbm" else peaks["bf16_tflops"],
+                     "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": max(fh, ft), "traffic": None,
+                     "alg_bytes": by, "dense_flops": flops, "frac_hbm": fh, "frac_tensor": ft, "single_kernel": True})
     return rows

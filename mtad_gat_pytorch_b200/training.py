@@ -75,6 +75,8 @@ class TrainStep:
         allreduce_gradients(self.params, self.world)
 
     def _capture(self):
+        # warm-up and capture on the SAME stream: the library's GEMM pack workspaces are per stream and cannot grow
+        # during capture (include/mtadgat.h: mtadgat_workspace_reserve)
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -85,15 +87,15 @@ class TrainStep:
         F.reset_launch_count()
         if self.world == 1:
             self.g_fb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_fb):
+            with torch.cuda.graph(self.g_fb, stream=s):
                 self._fwd_bwd()
                 self.opt.step()
         else:
             self.g_fb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_fb):
+            with torch.cuda.graph(self.g_fb, stream=s):
                 self._fwd_bwd()
             self.g_opt = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.g_opt):
+            with torch.cuda.graph(self.g_opt, stream=s):
                 self.opt.step()
         self.launches_per_step = F.launch_count()
 

@@ -15,7 +15,7 @@ with torch.no_grad():
     with torch.cuda.stream(s):
         m(x)
     torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
-    with torch.cuda.graph(g):
+    with torch.cuda.graph(g, stream=s):
         out = m(x)
     ts = []
     for _ in range(10):

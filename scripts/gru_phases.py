@@ -11,6 +11,8 @@ m = mg.MTAD_GAT(38, 100, 38, forecast_n_layers=3, dropout=0.3).cuda().train()
 m.branch_parallel = False
 x = torch.rand(256, 100, 38, device="cuda")
 names = ["mma.wait_h", "mma.issue+commit", "-", "epi.wait_acc", "epi.drain+bar1", "epi.math", "epi.st_async", "epi.tail(stores+prefetch)"]
+if len(sys.argv) > 1:
+    mg.set_gru_split(int(sys.argv[1]))
 for trial in range(2):
     p, r = m(x)
     torch.cuda.synchronize()

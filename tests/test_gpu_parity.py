@@ -426,3 +426,29 @@ def test_gru_layer_vs_torch_fp32_reference():
     assert rel(h, ref_h[-1].detach().cpu().numpy()) < TIGHT
     for a_, b_ in zip(g_mine, g_ref):
         assert rel(a_, b_.cpu().numpy()) < TIGHT
+
+
+@pytest.mark.parametrize("B", [5, 40])
+def test_cluster_recurrence_tile_split_is_invisible(B):
+    """The cluster recurrence may split a 16-window tile over 1, 2 or 4 clusters (mtadgat_set_gru_split); windows are
+    independent, so outputs are bit-identical and gradients agree (weight gradients go through atomics)."""
+    import mtad_gat_pytorch_b200 as mg
+    torch.manual_seed(3)
+    k, n = 38, 100
+    m = mg.MTAD_GAT(k, n, k, forecast_n_layers=3, dropout=0.0).cuda().train()
+    x = torch.rand(B, n, k, device="cuda")
+    y = torch.rand(B, 1, k, device="cuda")
+    res = {}
+    try:
+        for split in (1, 2, 4):
+            mg.set_gru_split(split)
+            m.zero_grad(set_to_none=True)
+            p, r = m(x)
+            loss_fn(x, y, p, r, None).backward()
+            res[split] = (p.detach().clone(), r.detach().clone(), {nm: q.grad.clone() for nm, q in m.named_parameters()})
+    finally:
+        mg.set_gru_split(0)
+    for split in (2, 4):
+        assert torch.equal(res[split][0], res[1][0]) and torch.equal(res[split][1], res[1][1]), split
+        for nm, g1 in res[1][2].items():
+            assert rel(res[split][2][nm], g1.cpu().numpy()) < 1e-5, (split, nm)
