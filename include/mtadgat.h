@@ -93,6 +93,16 @@ int mtadgat_linear_bwd(const float* x, const float* w, const float* y, const flo
                        int M, int I, int O, int act, float p_drop, const unsigned long long* seed,
                        unsigned int rng_stream, int parts, void* stream);
 
+/* ---- the training loss of the reference step (training.py:113-124), both terms in one pass:
+ *      losses[0] = sqrt(mean((y - preds)^2)) over n_pred elements, losses[1] = sqrt(mean((x - recons)^2)) over n_rec.
+ *      sums: 2 doubles of scratch.  bwd: dpreds = g_forecast * (preds - y) / (n_pred * losses[0]) (same for recons);
+ *      g_* are device scalars (the upstream gradients), dpreds / drecons nullable. ---- */
+int mtadgat_rmse_pair_fwd(const float* preds, const float* y, long long n_pred, const float* recons, const float* x,
+                          long long n_rec, float* losses, double* sums, void* stream);
+int mtadgat_rmse_pair_bwd(const float* preds, const float* y, long long n_pred, const float* recons, const float* x,
+                          long long n_rec, const float* losses, const float* g_forecast, const float* g_recon,
+                          float* dpreds, float* drecons, void* stream);
+
 /* ---- recurrence implementation: 1 (default) = persistent tcgen05/TMEM kernel, fp16 operands with fp32
  *      accumulation and fp32 hidden state (hidden sizes 8..256); 0 = fp32 SIMT kernel.  mtadgat_tc_probe runs one
  *      128 x N x K product through the same shared-memory operand layout (diagnostic / unit test). ---- */

@@ -40,6 +40,8 @@ SIGNATURES = {
     "mtadgat_gru_rep_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mtadgat_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _U, _P]),
     "mtadgat_linear_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _P, _U, _I, _P]),
+    "mtadgat_rmse_pair_fwd": (_I, [_P, _P, _LL, _P, _P, _LL, _P, _P, _P]),
+    "mtadgat_rmse_pair_bwd": (_I, [_P, _P, _LL, _P, _P, _LL, _P, _P, _P, _P, _P, _P]),
     "mtadgat_set_gemm_impl": (_I, [_I]),
     "mtadgat_get_gemm_impl": (_I, []),
     "mtadgat_workspace_reserve": (_I, [_P, _LL]),

@@ -231,6 +231,11 @@ struct StNodeAcc {
     *q = accumulate ? (*q + v) : v;
   }
 };
+}  // namespace
+namespace tcg2 {
+template <> struct NFast<StNodeAcc<true>> { static constexpr bool value = false; };   // feature layer: node (m) contiguous
+}
+namespace {
 // dV(b,j,dd) += sum_i att~[b][i][j] dS[b][i][dd]     batched over b;  att~ = att * dropout multiplier
 struct AttTA {
   static constexpr bool fast_second = false;     // m(j)-fast

@@ -109,6 +109,9 @@ struct StCat3T {
 
 }  // namespace
 
+namespace tcg2 {
+template <> struct NFast<StTiledBias> { static constexpr bool value = false; };   // window-tiled output: rows (m) contiguous
+}
 // ---- tensor-core loader specialisations (tc_gemm.cuh operand protocol) for the GRU functors ------------------
 namespace tcg {
 template <> struct OpA<Cat3AT> {

@@ -285,9 +285,13 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P
     const int nvalid_w = max(0, min(WPT, P.B - (b0 + wb)));
     const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
 
-    // input-side pre-activations of step `tt` (independent of the recurrence): software-pipelined one step ahead
+    // input-side pre-activations of step `tt` (independent of the recurrence), software-pipelined one step ahead:
+    // issue_inputs only ISSUES the global loads (their results are first touched by finish_inputs, in the math phase of
+    // the next step, so their latency hides behind the MMAs)
     float gr[WPT], gz[WPT], gn[WPT];
-    auto load_inputs = [&](int tt) {
+    float sra = 0.f, sza = 0.f, sna = 0.f, srb = 0.f, szb = 0.f, snb = 0.f, vbf = 0.f;
+    int seg_a = 0, seg_b = 0;
+    auto issue_inputs = [&](int tt) {
       if (P.gi) {
         if (valid) {
           const float* p = gi_p + (size_t)tt * gi_step;
@@ -296,33 +300,44 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P
 #pragma unroll
           for (int w = 0; w < WPT; ++w) { gr[w] = 0.f; gz[w] = 0.f; gn[w] = 0.f; }
         }
-      } else {
-        const int m0 = (int)(((long long)tt * P.Hs) / n);
-#pragma unroll
-        for (int w = 0; w < WPT; ++w) { gr[w] = bir; gz[w] = biz; gn[w] = bin; }
-        if (valid)
-          for (int j = 0; j < P.J; j += 2) {
-            // two segments per trip, all six weight loads issued before the first use (one L2 round trip for J <= 2)
-            const int ma = m0 + j;
-            if (ma >= P.Hs) break;
-            const bool vb = (j + 1 < P.J) && (ma + 1 < P.Hs);
-            const int mb = vb ? ma + 1 : ma;
-            const float* spa = P.S + ((size_t)tt * P.J + j) * G + u;
-            const float* spb = vb ? spa + G : spa;
-            const float sra = __ldg(spa), sza = __ldg(spa + H), sna = __ldg(spa + 2 * H);
-            float srb = __ldg(spb), szb = __ldg(spb + H), snb = __ldg(spb + 2 * H);
-            if (!vb) { srb = 0.f; szb = 0.f; snb = 0.f; }
-#pragma unroll
-            for (int w = 0; w < WPT; ++w) {
-              const float ha = sHs[(wb + w) * P.Hs + ma], hb = sHs[(wb + w) * P.Hs + mb];
-              gr[w] = fmaf(hb, srb, fmaf(ha, sra, gr[w]));
-              gz[w] = fmaf(hb, szb, fmaf(ha, sza, gz[w]));
-              gn[w] = fmaf(hb, snb, fmaf(ha, sna, gn[w]));
-            }
-          }
+      } else if (valid) {
+        // decoder: gi = b_ih + sum_j h_src[m0+j] S[tt][j]; the first two segments' weights are prefetched
+        seg_a = (int)(((long long)tt * P.Hs) / n);
+        const bool vb = (P.J > 1) && (seg_a + 1 < P.Hs);
+        seg_b = vb ? seg_a + 1 : seg_a;
+        vbf = vb ? 1.f : 0.f;
+        const float* spa = P.S + ((size_t)tt * P.J) * G + u;
+        const float* spb = vb ? spa + G : spa;
+        sra = __ldg(spa); sza = __ldg(spa + H); sna = __ldg(spa + 2 * H);
+        srb = __ldg(spb); szb = __ldg(spb + H); snb = __ldg(spb + 2 * H);
       }
     };
-    load_inputs(0);
+    auto finish_inputs = [&](int tt) {
+      if (P.gi) return;
+#pragma unroll
+      for (int w = 0; w < WPT; ++w) { gr[w] = bir; gz[w] = biz; gn[w] = bin; }
+      if (!valid) return;
+      const float rb = srb * vbf, zb = szb * vbf, nb = snb * vbf;
+#pragma unroll
+      for (int w = 0; w < WPT; ++w) {
+        const float ha = sHs[(wb + w) * P.Hs + seg_a], hb = sHs[(wb + w) * P.Hs + seg_b];
+        gr[w] = fmaf(hb, rb, fmaf(ha, sra, gr[w]));
+        gz[w] = fmaf(hb, zb, fmaf(ha, sza, gz[w]));
+        gn[w] = fmaf(hb, nb, fmaf(ha, sna, gn[w]));
+      }
+      for (int j = 2; j < P.J; ++j) {            // long segments lists (n < Hs): rare, not prefetched
+        const int m = seg_a + j;
+        if (m >= P.Hs) break;
+        const float* sp = P.S + ((size_t)tt * P.J + j) * G + u;
+        const float sr = __ldg(sp), sz = __ldg(sp + H), sn = __ldg(sp + 2 * H);
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) {
+          const float hv = sHs[(wb + w) * P.Hs + m];
+          gr[w] = fmaf(hv, sr, gr[w]); gz[w] = fmaf(hv, sz, gz[w]); gn[w] = fmaf(hv, sn, gn[w]);
+        }
+      }
+    };
+    issue_inputs(0);
 
     long long c_acc = 0, c_drain = 0, c_math = 0, c_st = 0, c_tail = 0;
     for (int t = 0; t < n; ++t) {
@@ -351,6 +366,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P
       named_bar_sync(1, EPI_THREADS);
       long long e3 = clock64(), e4 = e3;
       float rr[WPT], zz[WPT], nv[WPT], hv_[WPT];
+      finish_inputs(t);
       if (valid) {
         float arr[WPT], azz[WPT], ann[WPT];
         ld_w<WPT>(sG + (size_t)i * SG_LD + wb, arr);
@@ -385,7 +401,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P
           st_w<WPT>(gq + (size_t)3 * H * 16, hv_);
         }
       }
-      if (t + 1 < n) load_inputs(t + 1);
+      if (t + 1 < n) issue_inputs(t + 1);
       // the staging buffer is rewritten by the next drain only after the next MMA, which needs every thread's
       // h slice -- i.e. every thread is past its staging reads: no second barrier needed
       long long e6 = clock64();

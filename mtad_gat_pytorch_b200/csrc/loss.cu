@@ -1,0 +1,75 @@
+// The training loss of the reference step (training.py:113-124) as two launches forward and one backward:
+//   forecast_loss = sqrt(mean((y - preds)^2)),  recon_loss = sqrt(mean((x - recons)^2))
+// instead of ~35 elementwise / reduction launches of the eager expression.
+#include "common.cuh"
+#include "../../include/mtadgat.h"
+
+namespace {
+
+// sums[0] += sum (a0-b0)^2 over n0 elements; sums[1] += sum (a1-b1)^2 over n1 elements  (double accumulators)
+__global__ void __launch_bounds__(256) sqdiff2_kernel(const float* __restrict__ a0, const float* __restrict__ b0, long long n0,
+                                                      const float* __restrict__ a1, const float* __restrict__ b1, long long n1,
+                                                      double* __restrict__ sums) {
+  __shared__ double red[2][8];
+  double s0 = 0.0, s1 = 0.0;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = i0; i < n0; i += stride) { float d = __ldg(a0 + i) - __ldg(b0 + i); s0 += (double)(d * d); }
+  for (long long i = i0; i < n1; i += stride) { float d = __ldg(a1 + i) - __ldg(b1 + i); s1 += (double)(d * d); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[0][w] = s0; red[1][w] = s1; }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[threadIdx.x][i];
+    atomicAdd(sums + threadIdx.x, t);
+  }
+}
+__global__ void rmse_finish_kernel(const double* __restrict__ sums, long long n0, long long n1, float* __restrict__ losses) {
+  if (threadIdx.x == 0) losses[0] = (float)sqrt(sums[0] / (double)n0);
+  if (threadIdx.x == 1) losses[1] = (float)sqrt(sums[1] / (double)n1);
+}
+// d a_i = g_i * (a_i - b_i) / (n_i * loss_i)      (g_i = upstream gradient of loss i, read from device memory)
+__global__ void __launch_bounds__(256) rmse_bwd_kernel(const float* __restrict__ a0, const float* __restrict__ b0, long long n0,
+                                                       const float* __restrict__ a1, const float* __restrict__ b1, long long n1,
+                                                       const float* __restrict__ losses, const float* __restrict__ g0,
+                                                       const float* __restrict__ g1, float* __restrict__ da0,
+                                                       float* __restrict__ da1) {
+  const float l0 = __ldg(losses), l1 = __ldg(losses + 1);
+  const float c0 = l0 > 0.f ? __ldg(g0) / ((float)n0 * l0) : 0.f;
+  const float c1 = l1 > 0.f ? __ldg(g1) / ((float)n1 * l1) : 0.f;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  if (da0) for (long long i = i0; i < n0; i += stride) da0[i] = c0 * (__ldg(a0 + i) - __ldg(b0 + i));
+  if (da1) for (long long i = i0; i < n1; i += stride) da1[i] = c1 * (__ldg(a1 + i) - __ldg(b1 + i));
+}
+
+}  // namespace
+
+extern "C" int mtadgat_rmse_pair_fwd(const float* preds, const float* y, long long n_pred, const float* recons,
+                                     const float* x, long long n_rec, float* losses, double* sums, void* stream) {
+  MG_CHECK_ARG(preds && y && recons && x && losses && sums, "rmse_pair_fwd: null pointer");
+  MG_CHECK_ARG(n_pred > 0 && n_rec > 0, "rmse_pair_fwd: empty input");
+  cudaStream_t s = (cudaStream_t)stream;
+  MG_CUDA(cudaMemsetAsync(sums, 0, 2 * sizeof(double), s));
+  int blocks = (int)min((long long)296, (max(n_pred, n_rec) + 1023) / 1024);
+  sqdiff2_kernel<<<max(blocks, 1), 256, 0, s>>>(preds, y, n_pred, recons, x, n_rec, sums);
+  MG_COUNT_LAUNCH();
+  rmse_finish_kernel<<<1, 32, 0, s>>>(sums, n_pred, n_rec, losses);
+  MG_COUNT_LAUNCH();
+  MG_CHECK_LAUNCH("rmse_pair_fwd");
+  return MTADGAT_OK;
+}
+
+extern "C" int mtadgat_rmse_pair_bwd(const float* preds, const float* y, long long n_pred, const float* recons,
+                                     const float* x, long long n_rec, const float* losses, const float* g_forecast,
+                                     const float* g_recon, float* dpreds, float* drecons, void* stream) {
+  MG_CHECK_ARG(preds && y && recons && x && losses && g_forecast && g_recon, "rmse_pair_bwd: null pointer");
+  MG_CHECK_ARG(dpreds || drecons, "rmse_pair_bwd: no output requested");
+  int blocks = (int)min((long long)296, (max(n_pred, n_rec) + 1023) / 1024);
+  rmse_bwd_kernel<<<max(blocks, 1), 256, 0, (cudaStream_t)stream>>>(preds, y, n_pred, recons, x, n_rec, losses, g_forecast,
+                                                                    g_recon, dpreds, drecons);
+  MG_COUNT_LAUNCH();
+  MG_CHECK_LAUNCH("rmse_pair_bwd");
+  return MTADGAT_OK;
+}

@@ -24,6 +24,10 @@ namespace tcg2 {
 constexpr int BM = 128, BK = 32, KG = BK / 8, NTHREADS = 256, STAGES = 3;
 template <int R> struct Tile { static constexpr int HALF = KG * R * 16, BYTES = 2 * HALF; };   // hi block, lo block
 
+// store functors whose output is contiguous along n (row-major C) get a transposed epilogue: the accumulator chunk
+// goes through shared memory so that a warp writes 128 contiguous bytes per row instead of 32 scattered words.
+// Specialise to false for m-contiguous outputs (then lane = row is already the coalesced mapping).
+template <class C> struct NFast { static constexpr bool value = true; };
 // functors whose value does not depend on the batch index z are packed once (specialise to true)
 template <class F> struct BatchInvariant { static constexpr bool value = false; };
 
@@ -165,18 +169,38 @@ __global__ void __launch_bounds__(NTHREADS) gemm2_kernel(const uint8_t* __restri
     tc::mbar_wait(accb, 0);
     tc::tc_fence_after();
     const int q = warp & 3, half = warp >> 2;
-    const int gm = m0 + q * 32 + lane;
+    if (NFast<CS>::value) {
+      // the pipeline stages are idle now (every MMA has completed): reuse them as per-warp transpose buffers
+      float* stg = reinterpret_cast<float*>(smem_raw) + warp * (32 * 33);
 #pragma unroll 1
-    for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
-      if (n0 + c0 >= N) break;
-      float v[16];
-      tc::tmem_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tc::tmem_ld_wait();
-      if (gm < M) {
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
+        if (n0 + c0 >= N) break;
+        float v[32];
+        tc::tmem_ld32(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          int gn = n0 + c0 + i;
-          if (gn < N) C(z, gm, gn, v[i], splitk != 0);
+        for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = v[i];
+        __syncwarp();
+        const int gn = n0 + c0 + lane;
+        const int rows = min(32, M - (m0 + q * 32));
+        if (gn < N)
+          for (int r = 0; r < rows; ++r) C(z, m0 + q * 32 + r, gn, stg[r * 33 + lane], splitk != 0);
+        __syncwarp();
+      }
+    } else {
+      const int gm = m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 16) {
+        if (n0 + c0 >= N) break;
+        float v[16];
+        tc::tmem_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tc::tmem_ld_wait();
+        if (gm < M) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            int gn = n0 + c0 + i;
+            if (gn < N) C(z, gm, gn, v[i], splitk != 0);
+          }
         }
       }
     }

@@ -291,6 +291,35 @@ class LinearFn(torch.autograd.Function):
         return dx, dw, db, None, None, None, None
 
 
+class RmsePairFn(torch.autograd.Function):
+    """(sqrt(mean((y - preds)^2)), sqrt(mean((x - recons)^2))) -- training.py:113-124 -- in two launches."""
+
+    @staticmethod
+    def forward(ctx, preds, y, recons, x):
+        preds, y, recons, x = _prep(preds, "preds"), _prep(y, "y"), _prep(recons, "recons"), _prep(x, "x")
+        if preds.numel() != y.numel() or recons.numel() != x.numel():
+            raise MtadGatLibraryError(f"rmse_pair: shape mismatch {tuple(preds.shape)} vs {tuple(y.shape)}, "
+                                      f"{tuple(recons.shape)} vs {tuple(x.shape)}")
+        losses = torch.empty(2, dtype=torch.float32, device=x.device)
+        sums = torch.empty(2, dtype=torch.float64, device=x.device)
+        check(lib.mtadgat_rmse_pair_fwd(preds.data_ptr(), y.data_ptr(), preds.numel(), recons.data_ptr(), x.data_ptr(),
+                                        recons.numel(), losses.data_ptr(), sums.data_ptr(), _stream()))
+        ctx.save_for_backward(preds, y, recons, x, losses)
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        preds, y, recons, x, losses = ctx.saved_tensors
+        g0 = _prep(g0.reshape(1)); g1 = _prep(g1.reshape(1))
+        dp = torch.empty_like(preds) if ctx.needs_input_grad[0] else None
+        dr = torch.empty_like(recons) if ctx.needs_input_grad[2] else None
+        if dp is not None or dr is not None:
+            check(lib.mtadgat_rmse_pair_bwd(preds.data_ptr(), y.data_ptr(), preds.numel(), recons.data_ptr(), x.data_ptr(),
+                                            recons.numel(), losses.data_ptr(), g0.data_ptr(), g1.data_ptr(), _ptr(dp),
+                                            _ptr(dr), _stream()))
+        return dp, None, dr, None
+
+
 def set_gru_impl(name):
     """'tc' (default): persistent tcgen05/TMEM recurrence, fp16 operands, fp32 accumulate + fp32 state;
     'fp32': SIMT fp32 recurrence."""
