@@ -96,6 +96,21 @@ __host__ __device__ __forceinline__ float philox_uniform(unsigned long long seed
   return (float)(v >> 8) * (1.0f / 16777216.0f);
 }
 
+// the four uniforms of counter block `ctr` (elements 4*ctr .. 4*ctr+3 of the stream): one Philox evaluation for four
+// consecutive elements -- bit-identical to philox_uniform(seed, stream, 4*ctr + j)
+__host__ __device__ __forceinline__ void philox_uniform4(unsigned long long seed, uint32_t stream, unsigned long long ctr,
+                                                         float (&u)[4]) {
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = stream, c3 = 0x9E3779B9u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  u[0] = (float)(c0 >> 8) * (1.0f / 16777216.0f); u[1] = (float)(c1 >> 8) * (1.0f / 16777216.0f);
+  u[2] = (float)(c2 >> 8) * (1.0f / 16777216.0f); u[3] = (float)(c3 >> 8) * (1.0f / 16777216.0f);
+}
+
 // multiplier applied to a kept/dropped element: 0 or 1/(1-p)   (torch.dropout semantics, modules.py:90)
 __device__ __forceinline__ float dropout_mult(const unsigned long long* seed_ptr, uint32_t stream,
                                               unsigned long long idx, float p, float inv_keep) {

@@ -621,6 +621,230 @@ __global__ void __launch_bounds__(256) gat_bwd2_kernel(Bwd2Params P) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// whole-window variant (K <= 128): one CTA owns a window.  The window's projections PQt[b] (NC x Kp floats, one
+// contiguous block) arrive with ONE bulk asynchronous copy, so the K*K*E score build runs without staging loops or
+// barriers, on
+//   sum_d s_d relu(z_d) = 0.5 sum_d s_d z_d + 0.5 sum_d s_d |z_d| ,   sum_d s_d z_d = (1-alpha) (p_i + q_j)
+// i.e. TWO instructions per (i,j,d) (add, add-|.|) instead of three:  e_ij = (0.5+0.5 alpha)(p_i+q_j) + 0.5 acc_ij.
+// Each thread owns an MI x MJ tile of pairs (MJ even).  Softmax: one warp per row, lanes own 4 consecutive columns so
+// one Philox evaluation serves up to four dropout decisions.  Aggregation: 4x4 (i,dd) register tiles from V staged in
+// the (now free) projection buffer.
+// ---------------------------------------------------------------------------------------------
+template <int MI, int MJ>
+__global__ void __launch_bounds__(256, 2) gat_score_win_kernel(ScoreParams P) {
+  extern __shared__ __align__(128) float smem[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int K = P.K, Kp = P.Kp, E = P.E, D = P.D, NC = P.NC;
+  const int Dp = (D + 3) & ~3;
+  const int pq_floats = max(NC * Kp + 16, K * Dp);
+  float* sPQ = smem;                                   // [NC][Kp] (+slack), later V [K][Dp]
+  float* sS = smem + ((pq_floats + 3) & ~3);           // [K][Kp]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sS + (size_t)K * Kp);
+  const uint32_t bytes = (uint32_t)NC * Kp * 4;
+  if (tid == 0) {
+    tc::mbar_init(bar, 1);
+    tc::fence_mbar_init();
+    tcg2::arrive_expect_tx(bar, bytes);
+    tcg2::bulk_g2s(tc::smem_u32(sPQ), P.pqt + (size_t)b * NC * Kp, bytes, bar);
+  }
+  __syncthreads();
+  tc::mbar_wait(bar, 0);
+  const int npos = P.v2 ? P.meta[0] : 0;
+
+  // ---- rank-1 part + bias ----
+  {
+    const float* pr = sPQ + (size_t)(2 * E) * Kp;
+    const float* qr = pr + Kp;
+    const float c1 = 0.5f + 0.5f * P.alpha;
+    for (int i = warp; i < K; i += 8) {
+      const float pi = pr[i];
+      for (int j = lane; j < K; j += 32) {
+        const float sv = pi + qr[j];
+        float e = P.v2 ? c1 * sv : (sv > 0.f ? sv : P.alpha * sv);
+        if (P.bias) e += __ldg(P.bias + (size_t)i * K + j);
+        sS[i * Kp + j] = e;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- K*K*E part ----
+  if (E > 0) {
+    const int ntj = (K + MJ - 1) / MJ, nmt = ((K + MI - 1) / MI) * ntj;
+    for (int mt = tid; mt < nmt; mt += 256) {
+      const int ti = mt / ntj, tj = mt - ti * ntj;
+      const float* pp = sPQ + ti * MI;
+      const float* qq = sPQ + (size_t)E * Kp + tj * MJ;
+      float acc[MI][MJ];
+#pragma unroll
+      for (int a = 0; a < MI; ++a)
+#pragma unroll
+        for (int c = 0; c < MJ; ++c) acc[a][c] = 0.f;
+      auto step = [&](int d, float (&pv)[MI], float (&qv)[MJ]) {
+        if constexpr (MI == 4) { float4 t = *reinterpret_cast<const float4*>(pp + d * Kp); pv[0] = t.x; pv[1] = t.y; pv[2] = t.z; pv[3] = t.w; }
+        else if constexpr (MI == 2) { float2 t = *reinterpret_cast<const float2*>(pp + d * Kp); pv[0] = t.x; pv[1] = t.y; }
+        else { pv[0] = pp[d * Kp]; }
+#pragma unroll
+        for (int c = 0; c < MJ; c += 2) {
+          float2 t = *reinterpret_cast<const float2*>(qq + d * Kp + c);
+          qv[c] = t.x; qv[c + 1] = t.y;
+        }
+      };
+      int d = 0;
+#pragma unroll 2
+      for (; d < npos; ++d) {
+        float pv[MI], qv[MJ];
+        step(d, pv, qv);
+#pragma unroll
+        for (int a = 0; a < MI; ++a)
+#pragma unroll
+          for (int c = 0; c < MJ; ++c) acc[a][c] += fabsf(pv[a] + qv[c]);
+      }
+#pragma unroll 2
+      for (; d < E; ++d) {
+        float pv[MI], qv[MJ];
+        step(d, pv, qv);
+#pragma unroll
+        for (int a = 0; a < MI; ++a)
+#pragma unroll
+          for (int c = 0; c < MJ; ++c) acc[a][c] -= fabsf(pv[a] + qv[c]);
+      }
+#pragma unroll
+      for (int a = 0; a < MI; ++a) {
+        const int i = ti * MI + a;
+        if (i >= K) continue;
+#pragma unroll
+        for (int c = 0; c < MJ; ++c) {
+          const int j = tj * MJ + c;
+          if (j < K) sS[i * Kp + j] += 0.5f * acc[a][c];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- stage V over the projections (free now); softmax meanwhile touches only sS ----
+  {
+    float* sV = sPQ;
+    const float* xw = P.x + (size_t)b * P.n * P.k;
+    if (P.feature) {                      // V[j][t] = x[b,t,j]
+      for (int t = warp; t < P.n; t += 8)
+        for (int j = lane; j < P.k; j += 32) sV[j * Dp + t] = __ldg(xw + (size_t)t * P.k + j);
+    } else {                              // V[j][dd] = x[b,j,dd]
+      for (int j = warp; j < P.n; j += 8)
+        for (int dd = lane; dd < P.k; dd += 32) sV[j * Dp + dd] = __ldg(xw + (size_t)j * P.k + dd);
+    }
+  }
+  // ---- row softmax, save attention, dropout: lane owns columns 4*lane .. 4*lane+3 ----
+  {
+    const unsigned long long seed = (P.p > 0.f) ? *P.seed : 0ull;
+    const int j0 = 4 * lane;
+    for (int i = warp; i < K; i += 8) {
+      float* row = sS + i * Kp;
+      float v[4];
+      float m = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { v[c] = (j0 + c < K) ? row[j0 + c] : -INFINITY; m = fmaxf(m, v[c]); }
+      m = warp_max(m);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { v[c] = (j0 + c < K) ? __expf(v[c] - m) : 0.f; sum += v[c]; }
+      sum = warp_sum(sum);
+      const float inv = 1.f / sum;
+      float* arow = P.att ? P.att + ((size_t)b * K + i) * Kp : nullptr;
+      float keep[4] = {1.f, 1.f, 1.f, 1.f};
+      if (P.p > 0.f && j0 < K) {
+        const unsigned long long e0 = ((unsigned long long)b * K + i) * K + j0;
+        float ua[4], ub[4] = {0.f, 0.f, 0.f, 0.f};
+        philox_uniform4(seed, P.stream, e0 >> 2, ua);
+        const int sh = (int)(e0 & 3);
+        if (sh) philox_uniform4(seed, P.stream, (e0 >> 2) + 1, ub);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int q = sh + c;                         // selects, not indexed loads: the arrays stay in registers
+          const float x0 = q < 4 ? ua[0] : ub[0], x1 = q < 4 ? ua[1] : ub[1], x2 = q < 4 ? ua[2] : ub[2],
+                      x3 = q < 4 ? ua[3] : ub[3];
+          const int r = q & 3;
+          const float u = r == 0 ? x0 : (r == 1 ? x1 : (r == 2 ? x2 : x3));
+          keep[c] = u >= P.p ? P.inv_keep : 0.f;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (j0 + c < K) {
+          const float av = v[c] * inv;
+          if (arow) arow[j0 + c] = av;
+          row[j0 + c] = av * keep[c];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- aggregate S = A~ V, h = sigmoid(S): 4x4 (i,dd) tiles ----
+  {
+    const float* sV = sPQ;
+    const int ntd = Dp >> 2, nagg = ((K + 3) >> 2) * ntd;
+    for (int mt = tid; mt < nagg; mt += 256) {
+      const int ti = mt / ntd, td = mt - ti * ntd;
+      float acc[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+      const float* ar = sS + (size_t)(ti * 4) * Kp;
+      const int r1 = min(ti * 4 + 1, K - 1) - ti * 4, r2 = min(ti * 4 + 2, K - 1) - ti * 4, r3 = min(ti * 4 + 3, K - 1) - ti * 4;
+#pragma unroll 2
+      for (int j = 0; j < K; ++j) {
+        const float4 vv = *reinterpret_cast<const float4*>(sV + j * Dp + td * 4);
+        const float a0 = ar[j], a1 = ar[r1 * Kp + j], a2 = ar[r2 * Kp + j], a3 = ar[r3 * Kp + j];
+        acc[0][0] = fmaf(a0, vv.x, acc[0][0]); acc[0][1] = fmaf(a0, vv.y, acc[0][1]); acc[0][2] = fmaf(a0, vv.z, acc[0][2]); acc[0][3] = fmaf(a0, vv.w, acc[0][3]);
+        acc[1][0] = fmaf(a1, vv.x, acc[1][0]); acc[1][1] = fmaf(a1, vv.y, acc[1][1]); acc[1][2] = fmaf(a1, vv.z, acc[1][2]); acc[1][3] = fmaf(a1, vv.w, acc[1][3]);
+        acc[2][0] = fmaf(a2, vv.x, acc[2][0]); acc[2][1] = fmaf(a2, vv.y, acc[2][1]); acc[2][2] = fmaf(a2, vv.z, acc[2][2]); acc[2][3] = fmaf(a2, vv.w, acc[2][3]);
+        acc[3][0] = fmaf(a3, vv.x, acc[3][0]); acc[3][1] = fmaf(a3, vv.y, acc[3][1]); acc[3][2] = fmaf(a3, vv.z, acc[3][2]); acc[3][3] = fmaf(a3, vv.w, acc[3][3]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = ti * 4 + a;
+        if (i >= K) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int dd = td * 4 + c;
+          if (dd >= D) continue;
+          const size_t o = P.feature ? ((size_t)b * P.n + dd) * P.k + i : ((size_t)b * P.n + i) * P.k + dd;
+          P.out[o] = sigmoidf_(acc[a][c]);
+        }
+      }
+    }
+  }
+}
+
+static size_t score_win_smem(const GatDims& d) {
+  const int Dp = (d.D + 3) & ~3;
+  size_t pq = (size_t)max(d.NC * d.Kp + 16, d.K * Dp);
+  pq = (pq + 3) & ~(size_t)3;
+  return sizeof(float) * (pq + (size_t)d.K * d.Kp) + 16;
+}
+template <int MI, int MJ>
+static void launch_score_win(const ScoreParams& P, int B, size_t smem, cudaStream_t s) {
+  cudaFuncSetAttribute(gat_score_win_kernel<MI, MJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  gat_score_win_kernel<MI, MJ><<<B, 256, smem, s>>>(P);
+  MG_COUNT_LAUNCH();
+}
+// pair-tile shape for the whole-window kernel: fewest sequential pair updates per thread, ties -> larger tile
+static void launch_score_win_auto(const ScoreParams& P, int B, size_t smem, cudaStream_t s) {
+  const int cand[4][2] = {{4, 10}, {4, 4}, {2, 4}, {2, 2}};
+  int best = 0; long long best_cost = -1;
+  for (int c = 0; c < 4; ++c) {
+    long long nmt = (long long)cdiv(P.K, cand[c][0]) * cdiv(P.K, cand[c][1]);
+    long long cost = (long long)cdiv(nmt, 256) * cand[c][0] * cand[c][1];
+    if (best_cost < 0 || cost < best_cost) { best = c; best_cost = cost; }
+  }
+  if (best == 0) launch_score_win<4, 10>(P, B, smem, s);
+  else if (best == 1) launch_score_win<4, 4>(P, B, smem, s);
+  else if (best == 2) launch_score_win<2, 4>(P, B, smem, s);
+  else launch_score_win<2, 2>(P, B, smem, s);
+}
+
 static int pick_score_tiles(const GatDims& d, int& RB, int& JT, int& DT, size_t& smem) {
   const size_t budget = 200 * 1024;
   // rows per CTA: the aggregation gives each thread one 4x4 (i,dd) tile -> RB <= 4*floor(256/ceil(D/4))
@@ -690,13 +914,19 @@ extern "C" int mtadgat_gat_fwd(const float* x, const float* lin_w, const float* 
     if (feature) launch_gemm_batched(B, d.NC, d.K, d.D, A, NodeB<true>{x, n, k}, C, s);
     else launch_gemm_batched(B, d.NC, d.K, d.D, A, NodeB<false>{x, n, k}, C, s);
   }
-  int RB, JT, DT; size_t smem;
-  MG_CHECK_ARG(pick_score_tiles(d, RB, JT, DT, smem) == 0, "gat_fwd: shape outside the kernel envelope (D=%d)", d.D);
+  int RB = 0, JT = 0, DT = 0; size_t smem = 0;
+  const bool win = d.K <= 128 && score_win_smem(d) <= 112 * 1024;    // whole-window CTA, two resident per SM
+  if (!win) MG_CHECK_ARG(pick_score_tiles(d, RB, JT, DT, smem) == 0, "gat_fwd: shape outside the kernel envelope (D=%d)", d.D);
   ScoreParams P;
   P.x = x; P.pqt = pqt; P.bias = bias; P.meta = meta; P.out = out; P.att = att;
   P.n = n; P.k = k; P.K = d.K; P.D = d.D; P.E = d.E; P.NC = d.NC; P.Kp = d.Kp;
   P.RB = RB; P.JT = JT; P.DT = DT; P.feature = feature; P.v2 = use_gatv2; P.alpha = alpha;
   P.p = training ? p_drop : 0.f; P.inv_keep = 1.f / (1.f - P.p); P.seed = seed; P.stream = feature ? 1u : 2u;
+  if (win) {
+    launch_score_win_auto(P, B, score_win_smem(d), s);
+    MG_CHECK_LAUNCH("gat_fwd");
+    return MTADGAT_OK;
+  }
   dim3 grid(cdiv(d.K, RB), B);
   // micro-tile choice: keep most of the 256 threads busy for small K
   long long mt44 = (long long)cdiv(RB, 4) * cdiv(min(JT, d.K), 4);

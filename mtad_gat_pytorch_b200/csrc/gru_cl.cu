@@ -205,11 +205,23 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P
   const int u0 = rank * Uc, nu = max(0, min(Uc, H - u0));
 
   // ---- one-time staging: this CTA's W_hh rows (3 gates x Uc units) -> fp16 canonical layout; h_0 = 0 ----
-  for (int idx = tid; idx < 128 * Kp; idx += CL_THREADS) {
-    int row = idx / Kp, k = idx - row * Kp;
-    int g = row / Uc, i = row - g * Uc;
-    float v = (g < 3 && i < nu && k < H) ? __ldg(P.w_hh + ((size_t)g * H + u0 + i) * H + k) : 0.f;
-    *reinterpret_cast<__half*>(sA + (size_t)(k >> 3) * lboA + (size_t)row * 16 + (k & 7) * 2) = __float2half_rn(v);
+  // (8 independent loads in flight per thread: the staging loop is latency-, not bandwidth-bound)
+  for (int base = 0; base < 128 * Kp; base += 8 * CL_THREADS) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * CL_THREADS + tid;
+      const int row = idx / Kp, k = idx - row * Kp;
+      const int g = row / Uc, i = row - g * Uc;
+      v[j] = (idx < 128 * Kp && g < 3 && i < nu && k < H) ? __ldg(P.w_hh + ((size_t)g * H + u0 + i) * H + k) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * CL_THREADS + tid;
+      const int row = idx / Kp, k = idx - row * Kp;
+      if (idx < 128 * Kp)
+        *reinterpret_cast<__half*>(sA + (size_t)(k >> 3) * lboA + (size_t)row * 16 + (k & 7) * 2) = __float2half_rn(v[j]);
+    }
   }
   for (int idx = tid; idx < (2 * KC * LBO_B) / 4; idx += CL_THREADS) reinterpret_cast<uint32_t*>(sB)[idx] = 0u;
   if (!P.gi)
@@ -461,11 +473,22 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_bwd_kernel(ClBwdParams P
   const int tile = cid / SPLIT, wo = (cid % SPLIT) * NW, b0 = tile * NB + wo;
   const int u0 = rank * Uc, nu = max(0, min(Uc, H - u0));
 
-  for (int idx = tid; idx < 64 * Kp; idx += CL_THREADS) {
-    int kk = idx >> 6, i = idx & 63;                        // i fastest: coalesced reads of W_hh rows
-    int gate = kk / Hp, uu = kk - gate * Hp;
-    float v = (i < nu && gate < 3 && uu < H) ? __ldg(P.w_hh + ((size_t)gate * H + uu) * H + u0 + i) : 0.f;
-    *reinterpret_cast<__half*>(sA + (size_t)(kk >> 3) * lboA + (size_t)i * 16 + (kk & 7) * 2) = __float2half_rn(v);
+  for (int base = 0; base < 64 * Kp; base += 8 * CL_THREADS) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * CL_THREADS + tid;
+      const int kk = idx >> 6, i = idx & 63;                // i fastest: coalesced reads of W_hh rows
+      const int gate = kk / Hp, uu = kk - gate * Hp;
+      v[j] = (idx < 64 * Kp && i < nu && gate < 3 && uu < H) ? __ldg(P.w_hh + ((size_t)gate * H + uu) * H + u0 + i) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * CL_THREADS + tid;
+      const int kk = idx >> 6, i = idx & 63;
+      if (idx < 64 * Kp)
+        *reinterpret_cast<__half*>(sA + (size_t)(kk >> 3) * lboA + (size_t)i * 16 + (kk & 7) * 2) = __float2half_rn(v[j]);
+    }
   }
   for (int idx = tid; idx < (2 * KC * LBO_B) / 4; idx += CL_THREADS) reinterpret_cast<uint32_t*>(sB)[idx] = 0u;
   if (tid == 0) {
@@ -624,8 +647,19 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_bwd_kernel(ClBwdParams P
 __global__ void absmax2_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, long long nb,
                                unsigned int* __restrict__ out_bits) {
   float m = 0.f;
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
-  if (a) for (long long j = i; j < na; j += stride) m = fmaxf(m, fabsf(a[j]));
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  if (a) {
+    if ((reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+      const float4* a4 = reinterpret_cast<const float4*>(a);
+      for (long long j = i; j < (na >> 2); j += stride) {
+        const float4 v = __ldg(a4 + j);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      }
+      for (long long j = (na & ~3ll) + i; j < na; j += stride) m = fmaxf(m, fabsf(a[j]));
+    } else {
+      for (long long j = i; j < na; j += stride) m = fmaxf(m, fabsf(a[j]));
+    }
+  }
   if (b) for (long long j = i; j < nb; j += stride) m = fmaxf(m, fabsf(b[j]));
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
@@ -697,7 +731,7 @@ int mtadgat_gru_cl_bwd_launch(const float* gates_t, const float* out, const floa
   ClGeom g;
   if (!cl_geom(H, g)) { mtadgat_set_error("gru_cl_bwd: unsupported hidden size %d", H); return MTADGAT_ERR_UNSUPPORTED; }
   cudaMemsetAsync(gmax_bits, 0, sizeof(unsigned int), s);
-  absmax2_kernel<<<148, 256, 0, s>>>(dout, dout ? (long long)B * n * H : 0, dh_last, dh_last ? (long long)B * H : 0, gmax_bits);
+  absmax2_kernel<<<592, 256, 0, s>>>(dout, dout ? (long long)B * n * H : 0, dh_last, dh_last ? (long long)B * H : 0, gmax_bits);
   MG_COUNT_LAUNCH();
   ClBwdParams P;
   P.gates = gates_t; P.out = out; P.w_hh = w_hh; P.dout = dout; P.dh_last = dh_last; P.gmax_bits = gmax_bits;
