@@ -21,10 +21,16 @@
 namespace {
 
 constexpr int NB = 16;
-constexpr int EPI_THREADS = 256;
-constexpr int CL_THREADS = EPI_THREADS + 32;      // + one MMA-issuing warp (warp 8)
+constexpr int EPI_THREADS = 160;                  // 4 threads per unit, Uc <= 40 units per CTA: warps 0..4
+constexpr int CL_THREADS = 288;                   // warps 5..8: up to four MMA-issuing warps (warp 8 = primary)
 constexpr int LBO_B = 256, SBO_B = 128;           // MN-major B operand: [k/8][w/8][k%8][w%8] fp16
 constexpr int SG_LD = 20;                         // staging row stride (floats): 16 windows + pad
+// tensor-memory map of both kernels: accumulator in columns [0,16), resident W_hh slice (fp16, two K per 32-bit
+// column) from column 16
+__host__ __device__ __forceinline__ int tmem_cols_for(int a_col0, int a_cols) {
+  int need = a_col0 + a_cols;
+  return need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512));
+}
 
 // ---- cluster / DSMEM primitives ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -182,9 +188,13 @@ static size_t cl_fwd_smem(int H, int Hs_rep) {
 // Small batches use small NW: more clusters (more SMs busy, or two clusters interleaving on one SM) and a shorter
 // per-step dependency chain; the MMA is operand-fetch bound, so its cost does not depend on how many of the 16
 // B-operand columns carry live windows.
-template <int WPT>
+// NI MMA-issuing warps (8, 7, ...): a tcgen05.mma costs its issuing thread ~65 cycles whatever its size, so the K
+// chain of a step is dealt round-robin to NI warps, each accumulating into its own 16-column accumulator; the drain
+// adds the partial sums.
+template <int WPT, int NI>
 __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P) {
   constexpr int NW = 4 * WPT, SPLIT = NB / NW;
+  constexpr int A_TMEM_COL0 = 16 * NI;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int H = P.H, G = 3 * H, n = P.n, CS = P.CS, Uc = P.Uc;
   const int Kp = (CS * Uc + 15) & ~15, KC = Kp / 8;
@@ -230,26 +240,42 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P
       sHs[idx] = (b0 + w < P.B) ? __ldg(P.hsrc + (size_t)(b0 + w) * P.Hs + m) : 0.f;
     }
   if (tid == 0) {
-    tc::mbar_init(acc_bar, 1);
+    tc::mbar_init(acc_bar, NI);            // one tcgen05.commit per issuing warp and step
     tc::mbar_init(h_bar, 1);               // per step: the issuer's arrive.expect_tx; h_t arrives as st.async tx-bytes
     tc::fence_mbar_init();
   }
-  if (warp == 8) tc::tmem_alloc(tmem_slot, 32);
+  const int tmem_cols = tmem_cols_for(A_TMEM_COL0, Kp / 2);
+  if (warp == 8) tc::tmem_alloc(tmem_slot, tmem_cols);
   fence_proxy_async_all();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  // ---- W_hh slice: shared memory -> tensor memory (A operand of every step's MMAs; row = TMEM lane) ----
+  if (warp < 8) {
+    const int q = warp & 3, row = q * 32 + lane, nkc_ = Kp / 16;
+    const int c_beg = (warp >> 2) ? nkc_ / 2 : 0, c_end = (warp >> 2) ? nkc_ : nkc_ / 2;
+    for (int c = c_beg; c < c_end; ++c) {
+      const uint4 lo = *reinterpret_cast<const uint4*>(sA + (size_t)(2 * c) * lboA + (size_t)row * 16);
+      const uint4 hi = *reinterpret_cast<const uint4*>(sA + (size_t)(2 * c + 1) * lboA + (size_t)row * 16);
+      const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      tc::tmem_st8(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(A_TMEM_COL0 + c * 8), r);
+    }
+    tc::tmem_st_wait();
+  }
   tc::tc_fence_before();
   __syncthreads();
   cluster_sync_all();                  // every CTA's barriers and B buffers are initialised before any remote access
   tc::tc_fence_after();
-  const uint32_t tbase = *tmem_slot;
 
-  if (warp == 8) {
-    // ================= MMA issuer (whole warp runs the loop; one elected lane issues) =================
+  if (warp >= 9 - NI) {
+    // ================= MMA issuers (whole warp runs the loop; one elected lane issues) =================
+    const int ii = 8 - warp;                                  // 0 = primary (arms the hand-off barrier)
     const uint32_t idesc = tc::make_idesc_f16(128, NB, 0, /*b_mn_major=*/1);
-    const uint64_t ad0 = tc::make_smem_desc(tc::smem_u32(sA), lboA, 128);
-    const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
-    const uint32_t ainc = (uint32_t)(2 * lboA) >> 4, binc = (uint32_t)(2 * LBO_B) >> 4;
+    const uint32_t binc = (uint32_t)(2 * LBO_B) >> 4;
     const int nkc = Kp / 16;
     const uint32_t tx_bytes = (uint32_t)H * NW * 2;          // the whole h_t (all CTAs' slices) lands in this buffer
+    const uint32_t dacc = tbase + (uint32_t)(16 * ii);
     long long c_wait = 0, c_issue = 0;
     for (int t = 0; t < n; ++t) {
       long long q0 = clock64();
@@ -260,21 +286,21 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P
       long long q1 = clock64();
       c_wait += q1 - q0;
       const uint64_t bd0 = tc::make_smem_desc(tc::smem_u32(sB) + (uint32_t)((t & 1) * KC * LBO_B), LBO_B, SBO_B);
-      uint32_t alo = alo0, blo = (uint32_t)bd0;
+      uint32_t blo = (uint32_t)bd0 + (uint32_t)ii * binc, aaddr = tbase + A_TMEM_COL0 + 8 * ii;
       const uint32_t bhi = (uint32_t)(bd0 >> 32);
-      for (int kc = 0; kc < nkc; ++kc) {
-        if (tc::elect_one()) tc::mma_f16_ss_lohi(tbase, alo, ahi, blo, bhi, idesc, kc > 0 ? 1u : 0u);
-        alo += ainc; blo += binc;
+      for (int kc = ii; kc < nkc; kc += NI) {
+        if (tc::elect_one()) tc::mma_f16_ts(dacc, aaddr, blo, bhi, idesc, kc >= NI ? 1u : 0u);
+        aaddr += 8 * NI; blo += NI * binc;
       }
       if (tc::elect_one()) {
         tc::mma_commit(acc_bar);
-        if (t + 1 < n) mbar_arrive_expect_tx(h_bar, tx_bytes);   // arm the phase that receives h_{t+1}
+        if (ii == 0 && t + 1 < n) mbar_arrive_expect_tx(h_bar, tx_bytes);   // arm the phase that receives h_{t+1}
       }
       __syncwarp();
       c_issue += clock64() - q1;
     }
-    if (P.dbg && blockIdx.x == 0 && lane == 0) { P.dbg[0] = c_wait / n; P.dbg[1] = c_issue / n; }
-  } else {
+    if (P.dbg && blockIdx.x == 0 && lane == 0 && ii == 0) { P.dbg[0] = c_wait / n; P.dbg[1] = c_issue / n; }
+  } else if (warp < EPI_THREADS / 32) {
     // ================= epilogue: thread = (local unit i, WPT windows) =================
     const int i = tid >> 2, wq = tid & 3, wb = WPT * wq;
     const bool valid = i < nu;
@@ -361,17 +387,27 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P
         e2 = clock64();
         float4* dst = reinterpret_cast<float4*>(sG + (size_t)(warp * 32 + lane) * SG_LD);
         if (WPT == 4) {
-          float v[16];
-          tc::tmem_ld16(tlane, v);
+          float v[NI][16];
+#pragma unroll
+          for (int a = 0; a < NI; ++a) tc::tmem_ld16(tlane + 16 * a, v[a]);
           tc::tmem_ld_wait();
-          dst[0] = make_float4(v[0], v[1], v[2], v[3]);   dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-          dst[2] = make_float4(v[8], v[9], v[10], v[11]); dst[3] = make_float4(v[12], v[13], v[14], v[15]);
+#pragma unroll
+          for (int a = 1; a < NI; ++a)
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[0][c] += v[a][c];
+          dst[0] = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);   dst[1] = make_float4(v[0][4], v[0][5], v[0][6], v[0][7]);
+          dst[2] = make_float4(v[0][8], v[0][9], v[0][10], v[0][11]); dst[3] = make_float4(v[0][12], v[0][13], v[0][14], v[0][15]);
         } else {
-          float v[8];
-          tc::tmem_ld8(tlane, v);
+          float v[NI][8];
+#pragma unroll
+          for (int a = 0; a < NI; ++a) tc::tmem_ld8(tlane + 16 * a, v[a]);
           tc::tmem_ld_wait();
-          dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-          if (WPT == 2) dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+          for (int a = 1; a < NI; ++a)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[0][c] += v[a][c];
+          dst[0] = make_float4(v[0][0], v[0][1], v[0][2], v[0][3]);
+          if (WPT == 2) dst[1] = make_float4(v[0][4], v[0][5], v[0][6], v[0][7]);
         }
         tc::tc_fence_before();
       }
@@ -432,7 +468,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_fwd_kernel(ClFwdParams P
   tc::tc_fence_before();
   __syncthreads();
   cluster_sync_all();                  // no CTA leaves while peers may still touch its shared memory
-  if (warp == 8) tc::tmem_dealloc(tbase, 32);
+  if (warp == 8) tc::tmem_dealloc(tbase, tmem_cols);
 }
 
 // ==========================================================================================================
@@ -452,9 +488,13 @@ static size_t cl_bwd_smem(int H) {
   return (size_t)KC * 64 * 16 + 2 * (size_t)KC * LBO_B + (size_t)64 * SG_LD * 4 + 128;
 }
 
-template <int WPT>
+// NI issuing warps as in the forward kernel; with at most 8 live windows (WPT < 4) the MMAs run at N = 8 so that two
+// accumulators fit in columns [0,16) next to the 240-column resident operand (256 TMEM columns in total)
+template <int WPT, int NI>
 __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_bwd_kernel(ClBwdParams P) {
   constexpr int NW = 4 * WPT, SPLIT = NB / NW;
+  constexpr int A_TMEM_COL0 = 16, NMMA = 16 / NI;        // NI = 2 -> N = 8 per accumulator (requires NW <= 8)
+  static_assert(NI == 1 || (NI == 2 && WPT < 4), "two accumulators need N = 8");
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int H = P.H, G = 3 * H, n = P.n, CS = P.CS, Uc = P.Uc;
   const int Hp = CS * Uc;                                   // padded gate width: k = gate*Hp + unit
@@ -492,44 +532,62 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_bwd_kernel(ClBwdParams P
   }
   for (int idx = tid; idx < (2 * KC * LBO_B) / 4; idx += CL_THREADS) reinterpret_cast<uint32_t*>(sB)[idx] = 0u;
   if (tid == 0) {
-    tc::mbar_init(acc_bar, 1);
+    tc::mbar_init(acc_bar, NI);
     tc::mbar_init(h_bar, 1);
     tc::fence_mbar_init();
   }
-  if (warp == 8) tc::tmem_alloc(tmem_slot, 32);
+  const int tmem_cols = tmem_cols_for(A_TMEM_COL0, Kp / 2);
+  if (warp == 8) tc::tmem_alloc(tmem_slot, tmem_cols);
   fence_proxy_async_all();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  // ---- W_hh^T slice: shared memory -> tensor memory.  M = 64 operand rows live in lanes 32*(i/16) + i%16:
+  //      lanes 0..15 of warp q carry rows 16q .. 16q+15, the other lanes write zeros to unused lanes ----
+  if (warp < 8) {
+    const int q = warp & 3, row = q * 16 + (lane & 15), nkc_ = Kp / 16;
+    const int c_beg = (warp >> 2) ? nkc_ / 2 : 0, c_end = (warp >> 2) ? nkc_ : nkc_ / 2;
+    for (int c = c_beg; c < c_end; ++c) {
+      uint4 lo = *reinterpret_cast<const uint4*>(sA + (size_t)(2 * c) * lboA + (size_t)row * 16);
+      uint4 hi = *reinterpret_cast<const uint4*>(sA + (size_t)(2 * c + 1) * lboA + (size_t)row * 16);
+      if (lane >= 16) { lo = make_uint4(0u, 0u, 0u, 0u); hi = lo; }
+      const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      tc::tmem_st8(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(A_TMEM_COL0 + c * 8), r);
+    }
+    tc::tmem_st_wait();
+  }
   tc::tc_fence_before();
   __syncthreads();
   cluster_sync_all();
   tc::tc_fence_after();
-  const uint32_t tbase = *tmem_slot;
 
-  if (warp == 8) {
-    const uint32_t idesc = tc::make_idesc_f16(64, NB, 0, /*b_mn_major=*/1);
-    const uint64_t ad0 = tc::make_smem_desc(tc::smem_u32(sA), lboA, 128);
-    const uint32_t alo0 = (uint32_t)ad0, ahi = (uint32_t)(ad0 >> 32);
-    const uint32_t ainc = (uint32_t)(2 * lboA) >> 4, binc = (uint32_t)(2 * LBO_B) >> 4;
+  if (warp >= 9 - NI) {
+    const int ii = 8 - warp;
+    const uint32_t idesc = tc::make_idesc_f16(64, NMMA, 0, /*b_mn_major=*/1);
+    const uint32_t binc = (uint32_t)(2 * LBO_B) >> 4;
     const int nkc = Kp / 16;
     const uint32_t tx_bytes = (uint32_t)3 * H * NW * 2;      // all CTAs' (dpr, dpz, dgh_n) slices for NW windows
-    if (n > 1 && tc::elect_one()) mbar_arrive_expect_tx(h_bar, tx_bytes);
+    const uint32_t dacc = tbase + (uint32_t)(NMMA * ii);
+    if (ii == 0 && n > 1 && tc::elect_one()) mbar_arrive_expect_tx(h_bar, tx_bytes);
     __syncwarp();
     for (int it = 0; it < n - 1; ++it) {
       tc::mbar_wait(h_bar, it & 1);
       tc::tc_fence_after();
       const uint64_t bd0 = tc::make_smem_desc(tc::smem_u32(sB) + (uint32_t)((it & 1) * KC * LBO_B), LBO_B, SBO_B);
-      uint32_t alo = alo0, blo = (uint32_t)bd0;
+      uint32_t blo = (uint32_t)bd0 + (uint32_t)ii * binc, aaddr = tbase + A_TMEM_COL0 + 8 * ii;
       const uint32_t bhi = (uint32_t)(bd0 >> 32);
-      for (int kc = 0; kc < nkc; ++kc) {
-        if (tc::elect_one()) tc::mma_f16_ss_lohi(tbase, alo, ahi, blo, bhi, idesc, kc > 0 ? 1u : 0u);
-        alo += ainc; blo += binc;
+      for (int kc = ii; kc < nkc; kc += NI) {
+        if (tc::elect_one()) tc::mma_f16_ts(dacc, aaddr, blo, bhi, idesc, kc >= NI ? 1u : 0u);
+        aaddr += 8 * NI; blo += NI * binc;
       }
       if (tc::elect_one()) {
         tc::mma_commit(acc_bar);
-        if (it + 1 < n - 1) mbar_arrive_expect_tx(h_bar, tx_bytes);
+        if (ii == 0 && it + 1 < n - 1) mbar_arrive_expect_tx(h_bar, tx_bytes);
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp < EPI_THREADS / 32) {
     const int i = tid >> 2, wq = tid & 3, wb = WPT * wq;
     const bool valid = i < nu;
     const int u = u0 + i;
@@ -592,6 +650,14 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_bwd_kernel(ClBwdParams P
               dst[0] = make_float4(v[0], v[1], v[2], v[3]);   dst[1] = make_float4(v[4], v[5], v[6], v[7]);
               dst[2] = make_float4(v[8], v[9], v[10], v[11]); dst[3] = make_float4(v[12], v[13], v[14], v[15]);
             }
+          } else if (NI == 2) {
+            float v[16];                                  // accumulator 0 in columns 0..7, accumulator 1 in 8..15
+            tc::tmem_ld16(tlane, v);
+            tc::tmem_ld_wait();
+            if (lane < 16) {
+              dst[0] = make_float4(v[0] + v[8], v[1] + v[9], v[2] + v[10], v[3] + v[11]);
+              if (WPT == 2) dst[1] = make_float4(v[4] + v[12], v[5] + v[13], v[6] + v[14], v[7] + v[15]);
+            }
           } else {
             float v[8];
             tc::tmem_ld8(tlane, v);
@@ -641,7 +707,7 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_bwd_kernel(ClBwdParams P
   tc::tc_fence_before();
   __syncthreads();
   cluster_sync_all();
-  if (warp == 8) tc::tmem_dealloc(tbase, 32);
+  if (warp == 8) tc::tmem_dealloc(tbase, tmem_cols);
 }
 
 __global__ void absmax2_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, long long nb,
@@ -720,9 +786,11 @@ int mtadgat_gru_cl_fwd_launch(const float* gi_t, const float* S, const float* hs
   P.dbg = g_dbg;
   const int split = pick_split(B, g.CS), nblocks = cdiv(B, NB) * split * g.CS;
   const size_t smem = cl_fwd_smem(H, gi_t ? 0 : Hs);
-  if (split == 4) return launch_cluster(gru_cl_fwd_kernel<1>, P, nblocks, g.CS, smem, s);
-  if (split == 2) return launch_cluster(gru_cl_fwd_kernel<2>, P, nblocks, g.CS, smem, s);
-  return launch_cluster(gru_cl_fwd_kernel<4>, P, nblocks, g.CS, smem, s);
+  // one issuing warp: measured (B200, H = 150) the K chain costs ~65 cycles per tcgen05.mma whether the MMAs share an
+  // accumulator or not, so extra issuers (NI = 2, 4: kept as template options) only add drain work in the forward kernel
+  if (split == 4) return launch_cluster(gru_cl_fwd_kernel<1, 1>, P, nblocks, g.CS, smem, s);
+  if (split == 2) return launch_cluster(gru_cl_fwd_kernel<2, 1>, P, nblocks, g.CS, smem, s);
+  return launch_cluster(gru_cl_fwd_kernel<4, 1>, P, nblocks, g.CS, smem, s);
 }
 
 int mtadgat_gru_cl_bwd_launch(const float* gates_t, const float* out, const float* w_hh, const float* dout,
@@ -738,7 +806,7 @@ int mtadgat_gru_cl_bwd_launch(const float* gates_t, const float* out, const floa
   P.dgi = dgi_t; P.dghn = dghn_t; P.B = B; P.n = n; P.H = H; P.CS = g.CS; P.Uc = g.Uc;
   const int split = pick_split(B, g.CS), nblocks = cdiv(B, NB) * split * g.CS;
   const size_t smem = cl_bwd_smem(H);
-  if (split == 4) return launch_cluster(gru_cl_bwd_kernel<1>, P, nblocks, g.CS, smem, s);
-  if (split == 2) return launch_cluster(gru_cl_bwd_kernel<2>, P, nblocks, g.CS, smem, s);
-  return launch_cluster(gru_cl_bwd_kernel<4>, P, nblocks, g.CS, smem, s);
+  if (split == 4) return launch_cluster(gru_cl_bwd_kernel<1, 2>, P, nblocks, g.CS, smem, s);
+  if (split == 2) return launch_cluster(gru_cl_bwd_kernel<2, 2>, P, nblocks, g.CS, smem, s);
+  return launch_cluster(gru_cl_bwd_kernel<4, 1>, P, nblocks, g.CS, smem, s);
 }
