@@ -54,48 +54,66 @@ static SavedLayout saved_layout(const GatDims& d, int Eraw, int training) {
 // ---------------------------------------------------------------------------------------------
 // meta ints: [0]=npos, [4 .. 4+E) = perm (sorted position -> original column), [4+E .. 4+2E) = inverse
 __global__ void gat_prep_perm_kernel(const float* __restrict__ a, int E, int* __restrict__ meta) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp: stable partition of the columns by sign(a) with ballot prefix counts
+  const int lane = threadIdx.x & 31;
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   int np = 0;
-  for (int e = 0; e < E; ++e)
-    if (a[e] > 0.f) { meta[4 + np] = e; meta[4 + E + e] = np; ++np; }
-  meta[0] = np;
-  int q = np;
-  for (int e = 0; e < E; ++e)
-    if (!(a[e] > 0.f)) { meta[4 + q] = e; meta[4 + E + e] = q; ++q; }
+  for (int e0 = 0; e0 < E; e0 += 32) np += __popc(__ballot_sync(0xffffffffu, e0 + lane < E && a[e0 + lane] > 0.f));
+  int pos_base = 0, neg_base = np;
+  for (int e0 = 0; e0 < E; e0 += 32) {
+    const int e = e0 + lane;
+    const bool in = e < E, pos = in && a[e] > 0.f;
+    const unsigned mp = __ballot_sync(0xffffffffu, pos), mn = __ballot_sync(0xffffffffu, in && !pos);
+    const unsigned lt = (1u << lane) - 1u;
+    if (in) {
+      const int q = pos ? pos_base + __popc(mp & lt) : neg_base + __popc(mn & lt);
+      meta[4 + q] = e; meta[4 + E + e] = q;
+    }
+    pos_base += __popc(mp); neg_base += __popc(mn);
+  }
+  if (lane == 0) meta[0] = np;
 }
 
 // v2: lin_w (E, 2D), lin_b (E), a (E).   v1: lin_w (E, D), lin_b (E), a (2E).
 __global__ void gat_prep_fill_kernel(const float* __restrict__ lin_w, const float* __restrict__ lin_b,
                                      const float* __restrict__ a, const int* __restrict__ meta, float alpha, int D,
-                                     int Eraw, int v2, float* __restrict__ wp, float* __restrict__ bp) {
+                                     int Eraw, int v2, float* __restrict__ wp, float* __restrict__ bp, int nblk_cols) {
   const int NC = v2 ? 2 * Eraw + 2 : 2;
   const int E = v2 ? Eraw : 0;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  int total = (D + 1) * NC;  // row D is the bias row
-  if (idx >= total) return;
-  int dd = idx / NC, c = idx - dd * NC;
-  float v;
-  if (c < 2 * E) {
+  if ((int)blockIdx.x < nblk_cols) {
+    // scaled, sign-sorted columns: one thread per element of rows 0..D (row D is the bias row)
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = (D + 1) * 2 * E;
+    if (idx >= total) return;
+    int dd = idx / (2 * E), c = idx - dd * (2 * E);
     int half = c >= E, ep = c - half * E;
     int e = meta[4 + ep];
-    float s = fabsf(a[e]) * (1.f - alpha);
-    if (dd < D) v = s * lin_w[(long long)e * 2 * D + half * D + dd];
-    else v = half ? s * lin_b[e] : 0.f;
-  } else {
-    int half = c - 2 * E;
-    float acc = 0.f;
-    if (v2) {
-      if (dd < D) for (int e = 0; e < Eraw; ++e) acc += a[e] * lin_w[(long long)e * 2 * D + half * D + dd];
-      else if (half) for (int e = 0; e < Eraw; ++e) acc += a[e] * lin_b[e];
-    } else {
-      const float* ah = a + half * Eraw;
-      if (dd < D) for (int e = 0; e < Eraw; ++e) acc += ah[e] * lin_w[(long long)e * D + dd];
-      else for (int e = 0; e < Eraw; ++e) acc += ah[e] * lin_b[e];
-    }
-    v = acc;
+    float sc = fabsf(a[e]) * (1.f - alpha);
+    float v;
+    if (dd < D) v = sc * lin_w[(long long)e * 2 * D + half * D + dd];
+    else v = half ? sc * lin_b[e] : 0.f;
+    if (dd < D) wp[(long long)dd * NC + c] = v;
+    else bp[c] = v;
+    return;
   }
-  if (dd < D) wp[(long long)dd * NC + c] = v;
-  else bp[c] = v;
+  // rank-1 channels: one warp per (dd, half): sum over the E original columns
+  const int w = (blockIdx.x - nblk_cols) * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (w >= (D + 1) * 2) return;
+  const int dd = w >> 1, half = w & 1;
+  float acc = 0.f;
+  if (v2) {
+    if (dd < D) for (int e = lane; e < Eraw; e += 32) acc += a[e] * lin_w[(long long)e * 2 * D + half * D + dd];
+    else if (half) for (int e = lane; e < Eraw; e += 32) acc += a[e] * lin_b[e];
+  } else {
+    const float* ah = a + half * Eraw;
+    if (dd < D) for (int e = lane; e < Eraw; e += 32) acc += ah[e] * lin_w[(long long)e * D + dd];
+    else for (int e = lane; e < Eraw; e += 32) acc += ah[e] * lin_b[e];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (dd < D) wp[(long long)dd * NC + 2 * E + half] = acc;
+    else bp[2 * E + half] = acc;
+  }
 }
 
 // one warp per original column e: chain dWp/dbp back to lin_w, lin_b, a
@@ -236,14 +254,12 @@ namespace tcg2 {
 template <> struct NFast<StNodeAcc<true>> { static constexpr bool value = false; };   // feature layer: node (m) contiguous
 }
 namespace {
-// dV(b,j,dd) += sum_i att~[b][i][j] dS[b][i][dd]     batched over b;  att~ = att * dropout multiplier
+// dV(b,j,dd) += sum_i att~[b][i][j] dS[b][i][dd]     batched over b;  att~ = att * dropout multiplier (written by bwd1)
 struct AttTA {
   static constexpr bool fast_second = false;     // m(j)-fast
-  const float* att; int K, Kp; float p, inv_keep; const unsigned long long* seed; uint32_t stream;
+  const float* attm; int K, Kp;
   __device__ __forceinline__ float operator()(int b, int j, int i) const {
-    float v = __ldg(att + ((long long)b * K + i) * Kp + j);
-    if (p > 0.f) v *= dropout_mult(seed, stream, ((unsigned long long)b * K + i) * K + j, p, inv_keep);
-    return v;
+    return __ldg(attm + ((long long)b * K + i) * Kp + j);
   }
 };
 struct DsB {
@@ -461,7 +477,7 @@ __global__ void __launch_bounds__(256) gat_score_fwd_kernel(ScoreParams P) {
 // ---------------------------------------------------------------------------------------------
 struct Bwd1Params {
   const float* x; const float* out; const float* gout; const float* att;
-  float* ds; float* de;
+  float* ds; float* de; float* attm;
   int n, k, K, D, Kp, RB, JT, feature;
   float p, inv_keep; const unsigned long long* seed; uint32_t stream;
 };
@@ -522,15 +538,44 @@ __global__ void __launch_bounds__(256) gat_bwd1_kernel(Bwd1Params P) {
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31, nw = nth >> 5;
+  const unsigned long long seed = (P.p > 0.f) ? *P.seed : 0ull;
   for (int i = warp; i < rb; i += nw) {
     const float* arow = P.att + ((size_t)b * K + i0 + i) * Kp;
+    float* mrow = P.attm + ((size_t)b * K + i0 + i) * Kp;      // att * dropout multiplier, for the dV GEMM
     float* drow = sD + i * Kp;
     float dot = 0.f;
-    for (int j = lane; j < K; j += 32) {
-      float da = drow[j];
-      if (P.p > 0.f) da *= dropout_mult(P.seed, P.stream, ((unsigned long long)b * K + i0 + i) * K + j, P.p, P.inv_keep);
-      drow[j] = da;
-      dot += __ldg(arow + j) * da;
+    // lanes own 4 consecutive columns per trip: one Philox evaluation covers up to four mask decisions
+    for (int j0 = 4 * lane; j0 < Kp; j0 += 128) {
+      float keep[4] = {1.f, 1.f, 1.f, 1.f};
+      if (P.p > 0.f && j0 < K) {
+        const unsigned long long e0 = ((unsigned long long)b * K + i0 + i) * K + j0;
+        float ua[4], ub[4] = {0.f, 0.f, 0.f, 0.f};
+        philox_uniform4(seed, P.stream, e0 >> 2, ua);
+        const int sh = (int)(e0 & 3);
+        if (sh) philox_uniform4(seed, P.stream, (e0 >> 2) + 1, ub);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int q = sh + c;
+          const float x0 = q < 4 ? ua[0] : ub[0], x1 = q < 4 ? ua[1] : ub[1], x2 = q < 4 ? ua[2] : ub[2],
+                      x3 = q < 4 ? ua[3] : ub[3];
+          const int r = q & 3;
+          const float u = r == 0 ? x0 : (r == 1 ? x1 : (r == 2 ? x2 : x3));
+          keep[c] = u >= P.p ? P.inv_keep : 0.f;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = j0 + c;
+        if (j < K) {
+          const float av = __ldg(arow + j);
+          const float da = drow[j] * keep[c];
+          drow[j] = da;
+          dot += av * da;
+          mrow[j] = av * keep[c];
+        } else if (j < Kp) {
+          mrow[j] = 0.f;
+        }
+      }
     }
     dot = warp_sum(dot);
     float* erow = P.de + ((size_t)b * K + i0 + i) * Kp;
@@ -592,13 +637,16 @@ __global__ void __launch_bounds__(256) gat_bwd2_kernel(Bwd2Params P) {
     float4 xv = *reinterpret_cast<const float4*>(pq + (size_t)(xoff + d0 + d) * Kp + r0 + rg * 4);
     const float* yrow = sY + d * Kp;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // x + y > 0  <=>  y > -x : one compare + one predicated add per element
+    const float n0 = -xv.x, n1 = -xv.y, n2 = -xv.z, n3 = -xv.w;
+#pragma unroll 4
     for (int c = 0; c < K; ++c) {
-      float y = yrow[c];
-      float4 w = *reinterpret_cast<const float4*>(sW + c * RBk + rg * 4);
-      a0 += (xv.x + y > 0.f) ? w.x : 0.f;
-      a1 += (xv.y + y > 0.f) ? w.y : 0.f;
-      a2 += (xv.z + y > 0.f) ? w.z : 0.f;
-      a3 += (xv.w + y > 0.f) ? w.w : 0.f;
+      const float y = yrow[c];
+      const float4 w = *reinterpret_cast<const float4*>(sW + c * RBk + rg * 4);
+      if (y > n0) a0 += w.x;
+      if (y > n1) a1 += w.y;
+      if (y > n2) a2 += w.z;
+      if (y > n3) a3 += w.w;
     }
     float sg = (d0 + d < npos) ? 1.f : -1.f;
     *reinterpret_cast<float4*>(dpq + (size_t)(xoff + d0 + d) * Kp + r0 + rg * 4) = make_float4(sg * a0, sg * a1, sg * a2, sg * a3);
@@ -884,9 +932,9 @@ extern "C" long long mtadgat_gat_saved_floats(int B, int n, int k, int E, int fe
 
 extern "C" long long mtadgat_gat_bwd_scratch_floats(int B, int n, int k, int E, int feature, int use_gatv2) {
   GatDims d = make_dims(B, n, k, E, feature, use_gatv2);
-  // ds (B,K,D) | de (B,K,Kp) | dpqt (B,NC,Kp) | dwp (D,NC) | dbp (NC)
+  // ds (B,K,D) | de (B,K,Kp) | dpqt (B,NC,Kp) | dwp (D,NC) | dbp (NC) | pad | attm (B,K,Kp)
   return (long long)((size_t)d.B * d.K * d.D + (size_t)d.B * d.K * d.Kp + (size_t)d.B * d.NC * d.Kp +
-                     (size_t)d.D * d.NC + d.NC + 16);
+                     (size_t)d.D * d.NC + d.NC + 16 + (size_t)d.B * d.K * d.Kp);
 }
 
 extern "C" int mtadgat_gat_fwd(const float* x, const float* lin_w, const float* lin_b, const float* a,
@@ -904,8 +952,9 @@ extern "C" int mtadgat_gat_fwd(const float* x, const float* lin_w, const float* 
   float* pqt = saved + L.pqt; float* att = training ? saved + L.att : nullptr;
   if (use_gatv2) { gat_prep_perm_kernel<<<1, 32, 0, s>>>(a, E, meta); MG_COUNT_LAUNCH(); }
   {
-    int total = (d.D + 1) * d.NC;
-    gat_prep_fill_kernel<<<cdiv(total, 256), 256, 0, s>>>(lin_w, lin_b, a, meta, alpha, d.D, E, use_gatv2, wp, bp);
+    const int nblk_cols = cdiv((long long)(d.D + 1) * 2 * d.E, 256), nblk_r1 = cdiv((d.D + 1) * 2, 8);
+    gat_prep_fill_kernel<<<nblk_cols + nblk_r1, 256, 0, s>>>(lin_w, lin_b, a, meta, alpha, d.D, E, use_gatv2, wp, bp,
+                                                             nblk_cols);
     MG_COUNT_LAUNCH();
   }
   {
@@ -955,6 +1004,7 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
   float* dpqt = de + (size_t)d.B * d.K * d.Kp;
   float* dwp = dpqt + (size_t)d.B * d.NC * d.Kp;
   float* dbp = dwp + (size_t)d.D * d.NC;
+  float* attm = dbp + (((size_t)d.NC + 15) & ~(size_t)3);
   const float inv_keep = 1.f / (1.f - p_drop);
   const uint32_t strm = feature ? 1u : 2u;
   const bool do_data = parts & 1, do_par = parts & 2;
@@ -970,7 +1020,7 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
       else { mtadgat_set_error("gat_bwd: shape outside the kernel envelope"); return MTADGAT_ERR_UNSUPPORTED; }
     }
     Bwd1Params P;
-    P.x = x; P.out = out; P.gout = gout; P.att = att; P.ds = ds; P.de = de;
+    P.x = x; P.out = out; P.gout = gout; P.att = att; P.ds = ds; P.de = de; P.attm = attm;
     P.n = n; P.k = k; P.K = d.K; P.D = d.D; P.Kp = d.Kp; P.RB = RB; P.JT = JT; P.feature = feature;
     P.p = p_drop; P.inv_keep = inv_keep; P.seed = seed; P.stream = strm;
     cudaFuncSetAttribute(gat_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1019,7 +1069,7 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
   }
   // ---- data gradient: dV = A~^T dS + dPQ Wp^T ----
   if (do_data) {
-    AttTA A{att, d.K, d.Kp, p_drop, inv_keep, seed, strm};
+    AttTA A{attm, d.K, d.Kp};
     DsB Bd{ds, d.K, d.D};
     if (feature) launch_gemm_batched(B, d.K, d.D, d.K, A, Bd, StNodeAcc<true>{dx, n, k, dx_accumulate}, s);
     else launch_gemm_batched(B, d.K, d.D, d.K, A, Bd, StNodeAcc<false>{dx, n, k, dx_accumulate}, s);
