@@ -68,6 +68,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// 4-byte asynchronous global -> shared copy (LDGSTS): staging loops issue all their copies back to back and wait once,
+// instead of paying one L2 round trip per loop iteration; any shared-memory destination (transposes, padded rows)
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based RNG: dropout masks are a pure function of (seed, stream, element index)
 // so forward and backward regenerate the same mask without storing it.

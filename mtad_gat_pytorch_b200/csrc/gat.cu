@@ -482,57 +482,98 @@ struct Bwd1Params {
   float p, inv_keep; const unsigned long long* seed; uint32_t stream;
 };
 
+template <int MI>
 __global__ void __launch_bounds__(256) gat_bwd1_kernel(Bwd1Params P) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.y, i0 = blockIdx.x * P.RB;
   const int rb = min(P.RB, P.K - i0);
   const int tid = threadIdx.x, nth = blockDim.x;
-  const int K = P.K, Kp = P.Kp, D = P.D, Dp = D + 1;
+  const int K = P.K, Kp = P.Kp, D = P.D, Dp = 4 * (((D + 3) >> 2) | 1);   // zero-padded rows of 4*odd floats: 16-byte loads of
+                                                                        // consecutive rows hit distinct bank groups
   float* sD = smem;                         // [RB][Kp]  dA
   float* sdS = sD + (size_t)P.RB * Kp;      // [RB][Dp]
   float* sV = sdS + (size_t)P.RB * Dp;      // [JT][Dp]
-  for (int idx = tid; idx < rb * D; idx += nth) {
-    int i, dd;
-    size_t o;
-    if (P.feature) { dd = idx / rb; i = idx - dd * rb; o = ((size_t)b * P.n + dd) * P.k + i0 + i; }
-    else { i = idx / D; dd = idx - i * D; o = ((size_t)b * P.n + i0 + i) * P.k + dd; }
-    float h = __ldg(P.out + o), g = __ldg(P.gout + o);
-    float v = g * h * (1.f - h);
-    sdS[i * Dp + dd] = v;
-    P.ds[((size_t)b * K + i0 + i) * D + dd] = v;
+  for (int base = 0; base < rb * Dp; base += 4 * nth) {
+    float hv[4], gv[4]; int ii[4], dv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {            // 8 independent loads in flight per thread
+      const int idx = base + u * nth + tid;
+      int i = 0, dd = D;
+      if (idx < rb * Dp) {
+        if (P.feature) { dd = idx / rb; i = idx - dd * rb; }
+        else { i = idx / Dp; dd = idx - i * Dp; }
+      }
+      ii[u] = i; dv[u] = (idx < rb * Dp) ? dd : -1;
+      hv[u] = 0.f; gv[u] = 0.f;
+      if (dd < D) {
+        size_t o = P.feature ? ((size_t)b * P.n + dd) * P.k + i0 + i : ((size_t)b * P.n + i0 + i) * P.k + dd;
+        hv[u] = __ldg(P.out + o); gv[u] = __ldg(P.gout + o);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (dv[u] < 0) continue;
+      const float v = gv[u] * hv[u] * (1.f - hv[u]);
+      if (dv[u] < D) P.ds[((size_t)b * K + i0 + ii[u]) * D + dv[u]] = v;
+      sdS[ii[u] * Dp + dv[u]] = v;
+    }
   }
   for (int j0 = 0; j0 < K; j0 += P.JT) {
     const int jt = min(P.JT, K - j0);
     __syncthreads();
     if (P.feature) {
-      for (int idx = tid; idx < jt * D; idx += nth) {
+      for (int idx = tid; idx < jt * Dp; idx += nth) {
         int t = idx / jt, j = idx - t * jt;
-        sV[j * Dp + t] = __ldg(P.x + ((size_t)b * P.n + t) * P.k + j0 + j);
+        if (t < D) cp_async4(sV + j * Dp + t, P.x + ((size_t)b * P.n + t) * P.k + j0 + j);
+        else sV[j * Dp + t] = 0.f;
       }
     } else {
-      for (int idx = tid; idx < jt * D; idx += nth) {
-        int j = idx / D, dd = idx - j * D;
-        sV[j * Dp + dd] = __ldg(P.x + ((size_t)b * P.n + j0 + j) * P.k + dd);
+      for (int idx = tid; idx < jt * Dp; idx += nth) {
+        int j = idx / Dp, dd = idx - j * Dp;
+        if (dd < D) cp_async4(sV + j * Dp + dd, P.x + ((size_t)b * P.n + j0 + j) * P.k + dd);
+        else sV[j * Dp + dd] = 0.f;
       }
     }
+    cp_async_wait_all();
     __syncthreads();
-    // micro tile 2 x 2 over (i, j)
-    const int ntj = (jt + 1) >> 1, nmt = ((rb + 1) >> 1) * ntj;
+    // micro tile MI x 4 over (i, j), rows / columns of a tile STRIDED (i = ti + a*nti, j = tj + c*ntj) so that the
+    // lanes of a warp read consecutive rows; the dd loop moves 16-byte vectors of both operands
+    const int ntj = (jt + 3) >> 2, nti = (rb + MI - 1) / MI, nmt = nti * ntj;
+    const int D4 = (D + 3) >> 2;
     for (int mt = tid; mt < nmt; mt += nth) {
-      int ti = mt / ntj, tj = mt - ti * ntj;
-      int ia = ti * 2, ib = min(ia + 1, rb - 1), ja = tj * 2, jb = min(ja + 1, jt - 1);
-      const float* s0 = sdS + ia * Dp; const float* s1 = sdS + ib * Dp;
-      const float* v0 = sV + ja * Dp; const float* v1 = sV + jb * Dp;
-      float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f;
-      for (int dd = 0; dd < D; ++dd) {
-        float x0 = s0[dd], x1 = s1[dd], y0 = v0[dd], y1 = v1[dd];
-        a00 = fmaf(x0, y0, a00); a01 = fmaf(x0, y1, a01); a10 = fmaf(x1, y0, a10); a11 = fmaf(x1, y1, a11);
+      const int ti = mt / ntj, tj = mt - ti * ntj;
+      const float4* sp[MI]; const float4* vp[4];
+#pragma unroll
+      for (int a = 0; a < MI; ++a) sp[a] = reinterpret_cast<const float4*>(sdS + min(ti + a * nti, rb - 1) * Dp);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) vp[c] = reinterpret_cast<const float4*>(sV + min(tj + c * ntj, jt - 1) * Dp);
+      float acc[MI][4];
+#pragma unroll
+      for (int a = 0; a < MI; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll 2
+      for (int d4 = 0; d4 < D4; ++d4) {
+        float4 xs[MI], ys[4];
+#pragma unroll
+        for (int a = 0; a < MI; ++a) xs[a] = sp[a][d4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ys[c] = vp[c][d4];
+#pragma unroll
+        for (int a = 0; a < MI; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            acc[a][c] = fmaf(xs[a].x, ys[c].x, fmaf(xs[a].y, ys[c].y, fmaf(xs[a].z, ys[c].z, fmaf(xs[a].w, ys[c].w, acc[a][c]))));
       }
-      sD[ia * Kp + j0 + ja] = a00;
-      if (ja + 1 < jt) sD[ia * Kp + j0 + ja + 1] = a01;
-      if (ia + 1 < rb) {
-        sD[(ia + 1) * Kp + j0 + ja] = a10;
-        if (ja + 1 < jt) sD[(ia + 1) * Kp + j0 + ja + 1] = a11;
+#pragma unroll
+      for (int a = 0; a < MI; ++a) {
+        const int i = ti + a * nti;
+        if (i >= rb) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = tj + c * ntj;
+          if (j < jt) sD[i * Kp + j0 + j] = acc[a][c];
+        }
       }
     }
   }
@@ -594,15 +635,19 @@ struct Bwd2Params {
   int K, Kp, E, NC, DT, RBk, v2, pass; float alpha;      // RBk: rows r per CTA (multiple of 4)
 };
 
-// grid: (channel tiles, row blocks, B)
+// grid: (channel tiles, row blocks, B).  Thread tile: 4 rows x 4 channels (16 accumulators): per column c one 16-byte
+// load of w (4 rows) and one of Y (4 channels, Y staged column-major [c][DTp]) feed 16 compare-and-add pairs, so the
+// loop is bound by FP issue rather than shared-memory wavefronts.
 __global__ void __launch_bounds__(256) gat_bwd2_kernel(Bwd2Params P) {
   extern __shared__ __align__(16) float smem[];
   const int b = blockIdx.z, d0 = blockIdx.x * P.DT, r0 = blockIdx.y * P.RBk;
   const int K = P.K, Kp = P.Kp, E = P.E, RBk = P.RBk;
   const int rbk = min(RBk, Kp - r0);          // rows handled here (multiple of 4; rows >= K are padding)
   const int tid = threadIdx.x, nth = blockDim.x;
+  const int DTp = (P.DT + 3) & ~3;
   float* sW = smem;                         // [K (c)][RBk (r local)]
-  float* sY = sW + (size_t)K * RBk;         // [DT+1][Kp]  (row DT = rank-1 channel of Y)
+  float* sY = sW + (size_t)K * RBk;         // [K (c)][DTp]   Y channels of this tile, column-major
+  float* sY1 = sY + (size_t)K * DTp;        // [Kp]           rank-1 channel of Y
   const float* pq = P.pqt + (size_t)b * P.NC * Kp;
   const float* de = P.de + (size_t)b * K * Kp;
   const int xoff = P.pass ? E : 0, yoff = P.pass ? 0 : E;
@@ -622,37 +667,57 @@ __global__ void __launch_bounds__(256) gat_bwd2_kernel(Bwd2Params P) {
       sW[c * RBk + rl] = de[(size_t)c * Kp + r0 + rl];
     }
   }
-  for (int idx = tid; idx < dt * Kp; idx += nth) {
+  // Y[c][d]: coalesced reads along c; channels beyond dt are padded with -inf-like values that never pass y > -x
+  for (int idx = tid; idx < DTp * Kp; idx += nth) {
     int d = idx / Kp, c = idx - d * Kp;
-    sY[idx] = pq[(size_t)(yoff + d0 + d) * Kp + c];
+    if (c < K) sY[c * DTp + d] = (d < dt) ? pq[(size_t)(yoff + d0 + d) * Kp + c] : -3.0e38f;
   }
-  for (int c = tid; c < Kp; c += nth) sY[P.DT * Kp + c] = pq[(size_t)y1 * Kp + c];
+  for (int c = tid; c < Kp; c += nth) sY1[c] = pq[(size_t)y1 * Kp + c];
   __syncthreads();
   const int npos = P.v2 ? P.meta[0] : 0;
-  const int nrg = rbk >> 2;
-  const int nitems = nrg * dt;
+  const int nrg = rbk >> 2, ndg = DTp >> 2;
+  const int nitems = dt > 0 ? nrg * ndg : 0;
   float* dpq = P.dpqt + (size_t)b * P.NC * Kp;
   for (int it = tid; it < nitems; it += nth) {
-    int d = it / nrg, rg = it - d * nrg;
-    float4 xv = *reinterpret_cast<const float4*>(pq + (size_t)(xoff + d0 + d) * Kp + r0 + rg * 4);
-    const float* yrow = sY + d * Kp;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    // x + y > 0  <=>  y > -x : one compare + one predicated add per element
-    const float n0 = -xv.x, n1 = -xv.y, n2 = -xv.z, n3 = -xv.w;
-#pragma unroll 4
-    for (int c = 0; c < K; ++c) {
-      const float y = yrow[c];
-      const float4 w = *reinterpret_cast<const float4*>(sW + c * RBk + rg * 4);
-      if (y > n0) a0 += w.x;
-      if (y > n1) a1 += w.y;
-      if (y > n2) a2 += w.z;
-      if (y > n3) a3 += w.w;
+    const int dg = it / nrg, rg = it - dg * nrg;
+    // nx[a][q] = -X[d0 + 4dg + q][r0 + 4rg + a]
+    float nx[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int d = dg * 4 + q;
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (d < dt) xv = *reinterpret_cast<const float4*>(pq + (size_t)(xoff + d0 + d) * Kp + r0 + rg * 4);
+      nx[0][q] = -xv.x; nx[1][q] = -xv.y; nx[2][q] = -xv.z; nx[3][q] = -xv.w;
     }
-    float sg = (d0 + d < npos) ? 1.f : -1.f;
-    *reinterpret_cast<float4*>(dpq + (size_t)(xoff + d0 + d) * Kp + r0 + rg * 4) = make_float4(sg * a0, sg * a1, sg * a2, sg * a3);
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[a][q] = 0.f;
+    const float* wp_ = sW + rg * 4;
+    const float* yp_ = sY + dg * 4;
+#pragma unroll 2
+    for (int c = 0; c < K; ++c) {
+      const float4 w = *reinterpret_cast<const float4*>(wp_ + c * RBk);
+      const float4 y = *reinterpret_cast<const float4*>(yp_ + c * DTp);
+      const float wv[4] = {w.x, w.y, w.z, w.w}, yv[4] = {y.x, y.y, y.z, y.w};
+      // x + y > 0  <=>  y > -x : one compare + one predicated add per element
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (yv[q] > nx[a][q]) acc[a][q] += wv[a];
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int d = dg * 4 + q;
+      if (d >= dt) continue;
+      const float sg = (d0 + d < npos) ? 1.f : -1.f;
+      *reinterpret_cast<float4*>(dpq + (size_t)(xoff + d0 + d) * Kp + r0 + rg * 4) =
+          make_float4(sg * acc[0][q], sg * acc[1][q], sg * acc[2][q], sg * acc[3][q]);
+    }
   }
   if (blockIdx.x == 0) {
-    const float* yrow = sY + P.DT * Kp;
     for (int rl = tid; rl < rbk; rl += nth) {
       const int r = r0 + rl;
       float acc = 0.f;
@@ -660,13 +725,105 @@ __global__ void __launch_bounds__(256) gat_bwd2_kernel(Bwd2Params P) {
         float xr = pq[(size_t)x1 * Kp + r];
         for (int c = 0; c < K; ++c) {
           float w = sW[c * RBk + rl];
-          float g = P.v2 ? P.alpha : ((xr + yrow[c] > 0.f) ? 1.f : P.alpha);
+          float g = P.v2 ? P.alpha : ((xr + sY1[c] > 0.f) ? 1.f : P.alpha);
           acc = fmaf(w, g, acc);
         }
       }
       dpq[(size_t)x1 * Kp + r] = acc;
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward 2, whole-window variant (K <= 128): one CTA owns a window and runs BOTH passes from one staging of
+// de (row stride Kp+1: conflict-free along rows and along columns) and of the projections transposed to
+// [node][channel] (so 16 consecutive channels of one node are four 16-byte broadcast loads).
+// Thread item = (row r, 16 channels): per column c one scalar w load, four vector Y loads, 16 compare-and-adds.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2) gat_bwd2_win_kernel(Bwd2Params P) {
+  extern __shared__ __align__(16) float smem[];
+  const int b = blockIdx.x;
+  const int K = P.K, Kp = P.Kp, E = P.E;
+  const int tid = threadIdx.x;
+  const int ldw = Kp + 1, Ep = (E + 3) & ~3, NCp = 2 * Ep;
+  float* sT = smem;                          // [K][NCp]  P channels at [0,E), Q channels at [Ep,Ep+E) of every node
+  float* sDe = sT + (size_t)K * NCp;         // [K][ldw]
+  float* sR = sDe + (size_t)K * ldw;         // [2][Kp]   rank-1 channels p, q
+  const float* pq = P.pqt + (size_t)b * P.NC * Kp;
+  const float* de = P.de + (size_t)b * K * Kp;
+  float* dpq = P.dpqt + (size_t)b * P.NC * Kp;
+  for (int idx = tid; idx < 2 * E * Kp; idx += 256) {
+    const int ch = idx / Kp, node = idx - ch * Kp;
+    if (node < K) cp_async4(sT + node * NCp + (ch < E ? ch : Ep + ch - E), pq + idx);
+  }
+  for (int idx = tid; idx < K * Kp; idx += 256) {
+    const int i = idx / Kp, j = idx - i * Kp;
+    if (j < K) cp_async4(sDe + i * ldw + j, de + idx);
+  }
+  for (int idx = tid; idx < 2 * Kp; idx += 256) cp_async4(sR + idx, pq + (size_t)(2 * E) * Kp + idx);
+  cp_async_wait_all();
+  __syncthreads();
+  const int npos = P.v2 ? P.meta[0] : 0;
+  const int ngrp = (E + 15) >> 4;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int xoff = pass ? E : 0;                        // channel offset in dPQt (global)
+    const int sx = pass ? Ep : 0, sy = pass ? 0 : Ep;     // operand offsets in sT
+    // w(r,c) = de[r][c] (pass 0) or de[c][r] (pass 1)
+    const int wr = pass ? 1 : ldw, wc = pass ? ldw : 1;
+    for (int it = tid; it < ngrp * K; it += 256) {
+      const int g = it / K, r = it - g * K;
+      const int dbase = g * 16, nd = min(16, E - dbase);
+      float nx[16], acc[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        nx[q] = (q < nd) ? -sT[r * NCp + sx + dbase + q] : 3.0e38f;      // padding channels never pass y > -x
+        acc[q] = 0.f;
+      }
+      const float* wp_ = sDe + r * wr;
+      const float* yp_ = sT + sy + dbase;
+      // E need not be a multiple of 4: the vector loads of the last group may read the neighbouring block / padding
+      // columns, whose results are discarded through nx = +huge
+#pragma unroll 2
+      for (int c = 0; c < K; ++c) {
+        const float w = wp_[c * wc];
+        const float4* yv = reinterpret_cast<const float4*>(yp_ + c * NCp);
+        const float4 y0 = yv[0], y1 = yv[1], y2 = yv[2], y3 = yv[3];
+        const float ys[16] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w, y2.x, y2.y, y2.z, y2.w, y3.x, y3.y, y3.z, y3.w};
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          if (ys[q] > nx[q]) acc[q] += w;
+      }
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        if (q < nd) {
+          const int d = dbase + q;
+          dpq[(size_t)(xoff + d) * Kp + r] = (d < npos) ? acc[q] : -acc[q];
+        }
+      }
+    }
+    // rank-1 channel of this pass + zero padding columns K..Kp of the written rows
+    for (int r = tid; r < Kp; r += 256) {
+      float acc = 0.f;
+      if (r < K) {
+        const float xr = sR[pass * Kp + r];
+        const float* yr = sR + (1 - pass) * Kp;
+        for (int c = 0; c < K; ++c) {
+          const float w = sDe[r * wr + c * wc];
+          const float gg = P.v2 ? P.alpha : ((xr + yr[c] > 0.f) ? 1.f : P.alpha);
+          acc = fmaf(w, gg, acc);
+        }
+      }
+      dpq[(size_t)(2 * E + pass) * Kp + r] = acc;
+    }
+    for (int idx = tid; idx < E * (Kp - K); idx += 256) {
+      const int d = idx / (Kp - K), r = K + idx - d * (Kp - K);
+      dpq[(size_t)(xoff + d) * Kp + r] = 0.f;
+    }
+  }
+}
+static size_t bwd2_win_smem(const GatDims& d) {
+  const int NCp = 2 * ((d.E + 3) & ~3);
+  return sizeof(float) * ((size_t)d.K * (NCp + 16) + (size_t)d.K * (d.Kp + 1) + 2 * (size_t)d.Kp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -777,11 +934,12 @@ __global__ void __launch_bounds__(256, 2) gat_score_win_kernel(ScoreParams P) {
     const float* xw = P.x + (size_t)b * P.n * P.k;
     if (P.feature) {                      // V[j][t] = x[b,t,j]
       for (int t = warp; t < P.n; t += 8)
-        for (int j = lane; j < P.k; j += 32) sV[j * Dp + t] = __ldg(xw + (size_t)t * P.k + j);
+        for (int j = lane; j < P.k; j += 32) cp_async4(sV + j * Dp + t, xw + (size_t)t * P.k + j);
     } else {                              // V[j][dd] = x[b,j,dd]
       for (int j = warp; j < P.n; j += 8)
-        for (int dd = lane; dd < P.k; dd += 32) sV[j * Dp + dd] = __ldg(xw + (size_t)j * P.k + dd);
+        for (int dd = lane; dd < P.k; dd += 32) cp_async4(sV + j * Dp + dd, xw + (size_t)j * P.k + dd);
     }
+    // (asynchronous copies: they land while the softmax below runs; waited for before the aggregation)
   }
   // ---- row softmax, save attention, dropout: lane owns columns 4*lane .. 4*lane+3 ----
   {
@@ -827,6 +985,7 @@ __global__ void __launch_bounds__(256, 2) gat_score_win_kernel(ScoreParams P) {
       }
     }
   }
+  cp_async_wait_all();
   __syncthreads();
   // ---- aggregate S = A~ V, h = sigmoid(S): 4x4 (i,dd) tiles ----
   {
@@ -1013,7 +1172,8 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
     int RB = min(d.K, 64), JT = min(d.K, 64);
     size_t smem;
     for (;;) {
-      smem = sizeof(float) * ((size_t)RB * d.Kp + (size_t)RB * (d.D + 1) + (size_t)JT * (d.D + 1));
+      const size_t Dp = (size_t)4 * (((d.D + 3) >> 2) | 1);
+      smem = sizeof(float) * ((size_t)RB * d.Kp + (size_t)RB * Dp + (size_t)JT * Dp);
       if (smem <= 200 * 1024) break;
       if (JT > 8) JT = (JT + 1) / 2;
       else if (RB > 1) RB = (RB + 1) / 2;
@@ -1023,8 +1183,14 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
     P.x = x; P.out = out; P.gout = gout; P.att = att; P.ds = ds; P.de = de; P.attm = attm;
     P.n = n; P.k = k; P.K = d.K; P.D = d.D; P.Kp = d.Kp; P.RB = RB; P.JT = JT; P.feature = feature;
     P.p = p_drop; P.inv_keep = inv_keep; P.seed = seed; P.stream = strm;
-    cudaFuncSetAttribute(gat_bwd1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    gat_bwd1_kernel<<<dim3(cdiv(d.K, RB), B), 256, smem, s>>>(P);
+    // 4x4 pair tiles when they keep most of the 256 threads busy, else 2x4
+    if ((long long)cdiv(RB, 4) * cdiv(JT, 4) >= 200) {
+      cudaFuncSetAttribute(gat_bwd1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      gat_bwd1_kernel<4><<<dim3(cdiv(d.K, RB), B), 256, smem, s>>>(P);
+    } else {
+      cudaFuncSetAttribute(gat_bwd1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      gat_bwd1_kernel<2><<<dim3(cdiv(d.K, RB), B), 256, smem, s>>>(P);
+    }
     MG_COUNT_LAUNCH();
   }
   // ---- dbias ----
@@ -1033,10 +1199,20 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
     launch_colsum(B, d.K * d.K, DeCols{de, d.K, d.Kp}, dbias, s);
   }
   // ---- bwd2 (two passes) ----
-  if (do_data) {
+  if (do_data && d.K <= 128 && bwd2_win_smem(d) <= 112 * 1024) {
+    Bwd2Params P;
+    P.pqt = pqt; P.de = de; P.meta = meta; P.dpqt = dpqt; P.K = d.K; P.Kp = d.Kp; P.E = d.E; P.NC = d.NC;
+    P.DT = 0; P.RBk = 0; P.v2 = use_gatv2; P.pass = 0; P.alpha = alpha;
+    const size_t smem = bwd2_win_smem(d);
+    cudaFuncSetAttribute(gat_bwd2_win_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    gat_bwd2_win_kernel<<<B, 256, smem, s>>>(P);
+    MG_COUNT_LAUNCH();
+  } else if (do_data) {
     // shared memory: de block [K][RBk] + Y tile [DT+1][Kp]; shrink the channel tile first, then the row block
     int DT = d.E > 0 ? d.E : 1, RBk = d.Kp;
-    auto need = [&](int dtv, int rbv) { return sizeof(float) * ((size_t)d.K * rbv + (size_t)(dtv + 1) * d.Kp); };
+    auto need = [&](int dtv, int rbv) {
+      return sizeof(float) * ((size_t)d.K * rbv + (size_t)d.K * ((dtv + 3) & ~3) + (size_t)d.Kp);
+    };
     while (need(DT, RBk) > 200 * 1024 && DT > 8) DT = (DT + 1) / 2;
     while (need(DT, RBk) > 200 * 1024 && RBk > 16) RBk = (((RBk + 1) / 2) + 3) & ~3;
     MG_CHECK_ARG(need(DT, RBk) <= 220 * 1024, "gat_bwd: K=%d too large", d.K);
