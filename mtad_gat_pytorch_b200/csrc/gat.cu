@@ -269,6 +269,43 @@ struct DsB {
     return __ldg(ds + ((long long)b * K + i) * D + dd);
   }
 };
+// ---- feature layer (few nodes, long feature vectors): the same two products computed TRANSPOSED, with the feature index
+//      dd on the 128-row M side and the K <= 64 nodes on the N side, so that no tile is mostly padding:
+//      dV^T(b)[dd][j] += sum_i dS[b][i][dd] att~[b][i][j]  +  sum_c Wp[dd][c] dPQt[b][c][j]
+struct DsTA {                                      // A(m=dd, kk=i) = dS[b][i][dd]      (m-fast)
+  static constexpr bool fast_second = false;
+  const float* ds; int K, D;
+  __device__ __forceinline__ float operator()(int b, int dd, int i) const { return __ldg(ds + ((long long)b * K + i) * D + dd); }
+};
+struct AttmB {                                     // B(kk=i, n=j) = att~[b][i][j]      (n-fast)
+  static constexpr bool fast_second = true;
+  const float* attm; int K, Kp;
+  __device__ __forceinline__ float operator()(int b, int i, int j) const { return __ldg(attm + ((long long)b * K + i) * Kp + j); }
+};
+struct WpA2 {                                      // A(m=dd, kk=c) = Wp[dd][c]         (kk-fast, batch-invariant)
+  static constexpr bool fast_second = true;
+  const float* wp; int NC;
+  __device__ __forceinline__ float operator()(int, int dd, int c) const { return __ldg(wp + (long long)dd * NC + c); }
+};
+struct DpqBn {                                     // B(kk=c, n=j) = dPQt[b][c][j]      (n-fast)
+  static constexpr bool fast_second = true;
+  const float* dpqt; int NC, Kp;
+  __device__ __forceinline__ float operator()(int b, int c, int j) const { return __ldg(dpqt + ((long long)b * NC + c) * Kp + j); }
+};
+template <bool FEATURE>
+struct StNodeT {                                   // C(m=dd, n=node)
+  float* dx; int n, k; int accumulate;
+  __device__ __forceinline__ void operator()(int b, int dd, int node, float v, bool) const {
+    float* q = dx + node_off<FEATURE>(b, node, dd, n, k);
+    *q = accumulate ? (*q + v) : v;
+  }
+};
+}  // namespace
+namespace tcg2 {
+template <> struct BatchInvariant<WpA2> { static constexpr bool value = true; };
+template <> struct NFast<StNodeT<false>> { static constexpr bool value = false; };   // temporal layout: dd (m) contiguous
+}
+namespace {
 // dbias[i][j] = sum_b de[b][i][j]
 struct DeCols {
   static constexpr bool fast_second = true;
@@ -1247,12 +1284,19 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
   if (do_data) {
     AttTA A{attm, d.K, d.Kp};
     DsB Bd{ds, d.K, d.D};
-    if (feature) launch_gemm_batched(B, d.K, d.D, d.K, A, Bd, StNodeAcc<true>{dx, n, k, dx_accumulate}, s);
-    else launch_gemm_batched(B, d.K, d.D, d.K, A, Bd, StNodeAcc<false>{dx, n, k, dx_accumulate}, s);
     DpqA A2{dpqt, d.NC, d.Kp};
     WpB B2{wp, d.NC};
-    if (feature) launch_gemm_batched(B, d.K, d.D, d.NC, A2, B2, StNodeAcc<true>{dx, n, k, 1}, s);
-    else launch_gemm_batched(B, d.K, d.D, d.NC, A2, B2, StNodeAcc<false>{dx, n, k, 1}, s);
+    if (feature && d.K <= 64) {
+      // transposed products: M = feature index (D rows), N = nodes
+      launch_gemm_batched(B, d.D, d.K, d.K, DsTA{ds, d.K, d.D}, AttmB{attm, d.K, d.Kp}, StNodeT<true>{dx, n, k, dx_accumulate}, s);
+      launch_gemm_batched(B, d.D, d.K, d.NC, WpA2{wp, d.NC}, DpqBn{dpqt, d.NC, d.Kp}, StNodeT<true>{dx, n, k, 1}, s);
+    } else if (feature) {
+      launch_gemm_batched(B, d.K, d.D, d.K, A, Bd, StNodeAcc<true>{dx, n, k, dx_accumulate}, s);
+      launch_gemm_batched(B, d.K, d.D, d.NC, A2, B2, StNodeAcc<true>{dx, n, k, 1}, s);
+    } else {
+      launch_gemm_batched(B, d.K, d.D, d.K, A, Bd, StNodeAcc<false>{dx, n, k, dx_accumulate}, s);
+      launch_gemm_batched(B, d.K, d.D, d.NC, A2, B2, StNodeAcc<false>{dx, n, k, 1}, s);
+    }
   }
   MG_CHECK_LAUNCH("gat_bwd");
   return MTADGAT_OK;
