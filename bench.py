@@ -33,7 +33,7 @@ WORKLOAD = "SMD-shape (k=38,n=100) MTAD_GAT train step fwd+bwd+Adam, batch 256/G
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload, from the `ncu --set full` capture
 # summarised in profiles/ (cold caches: ncu flushes L2 before every replay pass)
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {"gru_recurrence_bwd_kernel": 108.3e6, "gru_recurrence_fwd_kernel": 73.3e6}   # profiles/r1_final_gru_cl_raw.csv
 
 
 def load_peaks():

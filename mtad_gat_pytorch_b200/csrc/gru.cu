@@ -265,18 +265,32 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
 
 // ---- decoder input shortcut -----------------------------------------------------------------------
 // m0[t] = (t*Hs)//n ;  S[t][j][g] = sum_{c in [0,Hs): (t*Hs+c)//n == m0[t]+j} w_ih[g][c]
-__global__ void rep_build_S_kernel(const float* __restrict__ w_ih, int n, int Hs, int G, int J, float* __restrict__ S) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * J * G) return;
-  int g = idx % G, j = (idx / G) % J, t = idx / (G * J);
-  long long base = (long long)t * Hs;
-  int m = (int)(base / n) + j;
-  // c range with (base + c) / n == m  <=>  m*n <= base + c < (m+1)*n
-  long long lo = (long long)m * n - base, hi = (long long)(m + 1) * n - base;
-  int clo = (int)max(lo, 0LL), chi = (int)min(hi, (long long)Hs);
-  float acc = 0.f;
-  for (int c = clo; c < chi; ++c) acc += w_ih[(long long)g * Hs + c];
-  S[idx] = acc;
+// block = 32 gate rows staged in shared memory (coalesced), thread = (row, every 8th step): segment sums from smem
+__global__ void __launch_bounds__(256) rep_build_S_kernel(const float* __restrict__ w_ih, int n, int Hs, int G, int J,
+                                                          float* __restrict__ S) {
+  extern __shared__ float sw[];                  // [32][Hs + 1]
+  const int g0 = blockIdx.x * 32, ld = Hs + 1;
+  for (int idx = threadIdx.x; idx < 32 * Hs; idx += 256) {
+    int r = idx / Hs, c = idx - r * Hs;
+    sw[r * ld + c] = (g0 + r < G) ? __ldg(w_ih + (long long)(g0 + r) * Hs + c) : 0.f;
+  }
+  __syncthreads();
+  const int gl = threadIdx.x & 31, g = g0 + gl;
+  if (g >= G) return;
+  const float* row = sw + gl * ld;
+  for (int t = threadIdx.x >> 5; t < n; t += 8) {
+    const long long base = (long long)t * Hs;
+    const int m0 = (int)(base / n);
+    for (int j = 0; j < J; ++j) {
+      const int m = m0 + j;
+      // c range with (base + c) / n == m  <=>  m*n <= base + c < (m+1)*n
+      const long long lo = (long long)m * n - base, hi = (long long)(m + 1) * n - base;
+      const int clo = (int)max(lo, 0LL), chi = (int)min(hi, (long long)Hs);
+      float acc = 0.f;
+      for (int c = clo; c < chi; ++c) acc += row[c];
+      S[((long long)t * J + j) * G + g] = acc;
+    }
+  }
 }
 // dW_ih[g][c] = sum_t dS[t][(t*Hs+c)//n - m0[t]][g];   (t*Hs+c)//n - (t*Hs)//n = ((t*Hs)%n + c)//n, tracked incrementally
 __global__ void rep_dw_kernel(const float* __restrict__ dS, int n, int Hs, int G, int J, float* __restrict__ dw_ih) {
@@ -684,7 +698,12 @@ extern "C" int mtadgat_gru_rep_fwd(const float* h_src, const float* w_ih, const 
   const int G = 3 * R, J = rep_J(n, Hs);
   float* wt = saved; float* S = saved + al4((size_t)3 * R * R);
   float* gates = save ? S + al4((size_t)n * J * G) : nullptr;
-  rep_build_S_kernel<<<cdiv((long long)n * J * G, 256), 256, 0, s>>>(w_ih, n, Hs, G, J, S);
+  {
+    const size_t sm = sizeof(float) * 32 * ((size_t)Hs + 1);
+    MG_CHECK_ARG(sm <= 200 * 1024, "gru_rep_fwd: source width %d too large", Hs);
+    if (sm > 48 * 1024) cudaFuncSetAttribute(rep_build_S_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    rep_build_S_kernel<<<cdiv(G, 32), 256, sm, s>>>(w_ih, n, Hs, G, J, S);
+  }
   MG_COUNT_LAUNCH();
   int rc = run_recurrence_fwd(nullptr, S, h_src, b_ih, J, Hs, w_hh, b_hh, wt, out, nullptr, gates, B, n, R, s);
   if (rc) return rc;
