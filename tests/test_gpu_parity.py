@@ -452,3 +452,45 @@ def test_cluster_recurrence_tile_split_is_invisible(B):
         assert torch.equal(res[split][0], res[1][0]) and torch.equal(res[split][1], res[1][1]), split
         for nm, g1 in res[1][2].items():
             assert rel(res[split][2][nm], g1.cpu().numpy()) < 1e-5, (split, nm)
+
+
+def test_fused_rmse_pair_matches_torch_expression():
+    """mtadgat_rmse_pair_fwd/_bwd (training.py:113-124) vs the plain torch expression, values and gradients."""
+    from mtad_gat_pytorch_b200 import training as mgt
+    torch.manual_seed(5)
+    B, n, k = 37, 100, 38
+    x = torch.rand(B, n, k, device="cuda"); y = torch.rand(B, 1, k, device="cuda")
+    preds = torch.rand(B, k, device="cuda", requires_grad=True)
+    recons = torch.rand(B, n, k, device="cuda", requires_grad=True)
+    fl, rl = mgt.rmse_losses(x, y, preds, recons)
+    (2.0 * fl + 0.5 * rl).backward()
+    g_mine = (preds.grad.clone(), recons.grad.clone())
+    preds.grad = None; recons.grad = None
+    fl_ref = torch.sqrt(torch.mean((y.squeeze(1) - preds) ** 2)); rl_ref = torch.sqrt(torch.mean((x - recons) ** 2))
+    (2.0 * fl_ref + 0.5 * rl_ref).backward()
+    assert abs(float(fl) - float(fl_ref)) < 1e-6 and abs(float(rl) - float(rl_ref)) < 1e-6
+    assert rel(g_mine[0], preds.grad.cpu().numpy()) < 1e-5 and rel(g_mine[1], recons.grad.cpu().numpy()) < 1e-5
+
+
+def test_pack_workspace_cannot_grow_during_capture():
+    """The packed GEMM's per-stream workspace is grow-only and must exist before capture: a first call on a fresh stream
+    inside a capture fails loudly (nothing launched, message names mtadgat_workspace_reserve); after an eager call on
+    the same stream the capture succeeds."""
+    import mtad_gat_pytorch_b200 as mg
+    from mtad_gat_pytorch_b200._lib import MtadGatLibraryError
+    lin = mg.Forecasting_Model(64, 64, 64, 1, 0.0).cuda().eval()
+    x = torch.rand(300, 64, device="cuda")
+    s = torch.cuda.Stream()
+    g = torch.cuda.CUDAGraph()
+    with pytest.raises(MtadGatLibraryError, match="workspace"):
+        with torch.cuda.graph(g, stream=s):
+            lin(x)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        ref = lin(x)
+    torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2, stream=s):
+        out = lin(x)
+    g2.replay(); torch.cuda.synchronize()
+    assert torch.equal(out, ref)
