@@ -77,23 +77,27 @@ def dropout_multipliers(numel, p, seed_t, rng_stream):
 PARAM_SIDE_STREAM = True
 _param_streams = {}
 _join_pending = set()
+_param_rr = [0]
+N_PARAM_STREAMS = 2          # parameter-gradient work alternates between two side streams (one overloads late in backward)
 
 
-def _param_stream(device):
+def _param_stream_list(device):
     s = _param_streams.get(device)
     if s is None:
-        s = _param_streams[device] = torch.cuda.Stream(device=device)
+        s = _param_streams[device] = [torch.cuda.Stream(device=device) for _ in range(N_PARAM_STREAMS)]
     return s
 
 
 def _run_bwd(device, call, tensors):
-    """call(parts, stream_ptr): issue the data part here, the parameter part on the side stream."""
+    """call(parts, stream_ptr): issue the data part here, the parameter part on a side stream."""
     if not PARAM_SIDE_STREAM:
         call(3, _stream())
         return
     cur = torch.cuda.current_stream(device)
     call(1, cur.cuda_stream)
-    ps = _param_stream(device)
+    streams = _param_stream_list(device)
+    ps = streams[_param_rr[0] % len(streams)]
+    _param_rr[0] += 1
     ps.wait_stream(cur)
     call(2, ps.cuda_stream)
     for t in tensors:
@@ -104,7 +108,9 @@ def _run_bwd(device, call, tensors):
 
         def _join():
             _join_pending.discard(device)
-            torch.cuda.current_stream(device).wait_stream(ps)
+            _param_rr[0] = 0                  # same assignment every step (CUDA-graph capture and eager warm-up agree)
+            for st in streams:
+                torch.cuda.current_stream(device).wait_stream(st)
         torch.autograd.Variable._execution_engine.queue_callback(_join)
 
 

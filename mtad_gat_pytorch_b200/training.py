@@ -142,6 +142,34 @@ class TrainStep:
         fl, rl = self.losses.tolist()
         return fl + rl
 
+    def launch_prefetched(self):
+        """Enqueue the step on the oldest prefetched batch plus an asynchronous D2H copy of its two loss terms into
+        pinned host memory, without waiting: the host can enqueue step i+1 while step i runs.  collect() returns the
+        losses in launch order."""
+        slot = self._get & 1
+        self._get += 1
+        torch.cuda.current_stream().wait_event(self._staged[slot])
+        sx, sy = self._stage[slot]
+        self.x.copy_(sx); self.y.copy_(sy)
+        self._run()
+        if not hasattr(self, "_loss_host"):
+            self._loss_host = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._loss_ev = [None, None]
+            self._lput = self._lget = 0
+        k = self._lput & 1
+        self._lput += 1
+        self._loss_host[k].copy_(self.losses, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record()
+        self._loss_ev[k] = ev
+
+    def collect(self):
+        """Scalar loss of the oldest launched-but-uncollected step (waits for that step only)."""
+        k = self._lget & 1
+        self._lget += 1
+        self._loss_ev[k].synchronize()
+        v = self._loss_host[k]
+        return float(v[0]) + float(v[1])
+
     def run_host(self, x_host, y_host):
         """Pinned host batch in, scalar loss out (H2D + step + D2H)."""
         self.x.copy_(x_host, non_blocking=True); self.y.copy_(y_host, non_blocking=True)
