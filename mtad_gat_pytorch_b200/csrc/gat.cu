@@ -316,6 +316,65 @@ struct DeCols {
   }
 };
 
+}  // namespace
+// ---- packed-GEMM loader specialisations: the (b, node) decode of a K index is done once per 8 elements ----
+namespace tcg {
+template <bool FEATURE> struct OpA<NodeAT<FEATURE>> {      // A(m=dd, kk=(b,node)) = V(b,node,dd)
+  using F = NodeAT<FEATURE>;
+  struct Ctx { int dd; };
+  static __device__ __forceinline__ Ctx line(const F&, int, int dd) { return Ctx{dd}; }
+  static __device__ __forceinline__ void load8(const F& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    int b = k0 / f.K, node = k0 - b * f.K;
+    const float* p = f.x + node_off<FEATURE>(b, node, c.dd, f.n, f.k);
+    const long long step = FEATURE ? 1 : f.k;                                     // node -> node + 1
+    const long long wrap = (long long)f.n * f.k - (long long)f.K * step;            // last node of b -> node 0 of b + 1
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = (k0 + j < kend) ? __ldg(p) : 0.f;
+      p += step;
+      if (++node == f.K) { node = 0; p += wrap; }
+    }
+  }
+};
+template <> struct OpB<DpqB> {                             // B(kk=(b,node), n=c) = dPQt[b][c][node]
+  struct Ctx { int c; };
+  static __device__ __forceinline__ Ctx line(const DpqB&, int, int c) { return Ctx{c}; }
+  static __device__ __forceinline__ void load8(const DpqB& f, const Ctx& c, int, int k0, int kend, float (&v)[8]) {
+    int b = k0 / f.K, node = k0 - b * f.K;
+    const float* p = f.dpqt + ((long long)b * f.NC + c.c) * f.Kp + node;
+    const long long wrap = (long long)f.NC * f.Kp - f.K;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = (k0 + j < kend) ? __ldg(p) : 0.f;
+      ++p;
+      if (++node == f.K) { node = 0; p += wrap; }
+    }
+  }
+};
+}  // namespace tcg
+namespace {
+// dbp[c] += sum_{b, node < K} dPQt[b][c][node]: block = (channel c, slice of windows), warp per window
+__global__ void __launch_bounds__(256) dpq_colsum_kernel(const float* __restrict__ dpqt, int B, int NC, int K, int Kp, int bper,
+                                                         float* __restrict__ dbp) {
+  __shared__ float red[8];
+  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b0 = blockIdx.y * bper, b1 = min(B, b0 + bper);
+  float s = 0.f;
+  for (int b = b0 + warp; b < b1; b += 8) {
+    const float* row = dpqt + ((size_t)b * NC + c) * Kp;
+    for (int j = lane; j < K; j += 32) s += __ldg(row + j);
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    atomicAdd(dbp + c, t);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // fused score -> softmax -> dropout -> aggregate -> sigmoid       (one CTA = one window x RB rows)
 // ---------------------------------------------------------------------------------------------
@@ -1272,7 +1331,11 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
     StAtomic2 C{dwp, d.NC};
     if (feature) launch_gemm_splitk(d.D, d.NC, B * d.K, NodeAT<true>{x, n, k, d.K}, Bq, C, s);
     else launch_gemm_splitk(d.D, d.NC, B * d.K, NodeAT<false>{x, n, k, d.K}, Bq, C, s);
-    launch_colsum(B * d.K, d.NC, DpqCols{dpqt, d.NC, d.Kp, d.K}, dbp, s);
+    {
+      const int nsplit = max(1, min(cdiv(B, 8), cdiv(592, d.NC))), bper = cdiv(B, nsplit);
+      dpq_colsum_kernel<<<dim3(d.NC, cdiv(B, bper)), 256, 0, s>>>(dpqt, B, d.NC, d.K, d.Kp, bper, dbp);
+      MG_COUNT_LAUNCH();
+    }
   }
   if (do_par) {
     int nw = 8;
