@@ -39,6 +39,11 @@ int mtadgat_conv_relu_fwd(const float* x, const float* w, const float* bias, flo
                           void* stream);
 int mtadgat_conv_relu_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx /*nullable*/,
                           float* dw, float* db, int B, int n, int k, int ks, void* stream);
+/* same, for an output that feeds several consumers (mtad_gat.py:68-71: both GAT layers and the GRU read the conv
+ * output): the consumers' gradients dy, dy1, dy2 (dy1 / dy2 nullable) are summed inside the kernels */
+int mtadgat_conv_relu_bwd3(const float* x, const float* w, const float* y, const float* dy, const float* dy1,
+                           const float* dy2, float* dx /*nullable*/, float* dw, float* db, int B, int n, int k, int ks,
+                           void* stream);
 
 /* ---- FeatureAttentionLayer.forward modules.py:65-95 (feature=1) / TemporalAttentionLayer.forward
  *      modules.py:166-193 (feature=0).  E = lin.weight.shape[0]; GATv2: lin_w (E,2D), a (E); GATv1: lin_w (E,D),

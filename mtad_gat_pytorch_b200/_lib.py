@@ -23,6 +23,7 @@ SIGNATURES = {
     "mtadgat_reset_launch_count": (None, []),
     "mtadgat_conv_relu_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mtadgat_conv_relu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "mtadgat_conv_relu_bwd3": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mtadgat_gat_saved_floats": (_LL, [_I, _I, _I, _I, _I, _I, _I]),
     "mtadgat_gat_bwd_scratch_floats": (_LL, [_I, _I, _I, _I, _I, _I]),
     "mtadgat_gat_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _P, _P]),

@@ -11,6 +11,7 @@ template <bool MASKED>
 struct ConvShiftLoad {
   static constexpr bool fast_second = true;
   const float* src; const float* y; int n, k, pad, sgn;
+  const float* src1; const float* src2;          // MASKED only: further gradient sources (nullable)
   __device__ __forceinline__ float operator()(int, int m, int kk) const {
     int b = m / n, t = m - b * n;
     int tau = kk / k, c = kk - tau * k;
@@ -18,7 +19,11 @@ struct ConvShiftLoad {
     if (ts < 0 || ts >= n) return 0.f;
     long long o = ((long long)b * n + ts) * k + c;
     float v = __ldg(src + o);
-    if (MASKED) v = (__ldg(y + o) > 0.f) ? v : 0.f;
+    if (MASKED) {
+      if (src1) v += __ldg(src1 + o);
+      if (src2) v += __ldg(src2 + o);
+      v = (__ldg(y + o) > 0.f) ? v : 0.f;
+    }
     return v;
   }
 };
@@ -42,12 +47,20 @@ struct ConvWBwd {
   }
 };
 // A(m=co, kk=(b,t)) = dy[(b,t),co] * (y>0)        (weight gradient)
+// the layer output may feed several consumers (the two GAT layers and the GRU read it): their gradients dy, dy1, dy2
+// (dy1 / dy2 nullable) are summed on the fly instead of by separate add kernels
+__device__ __forceinline__ float dy_sum(const float* dy, const float* dy1, const float* dy2, long long o) {
+  float v = __ldg(dy + o);
+  if (dy1) v += __ldg(dy1 + o);
+  if (dy2) v += __ldg(dy2 + o);
+  return v;
+}
 struct DpreT {
   static constexpr bool fast_second = false;
-  const float* dy; const float* y; int k;
+  const float* dy; const float* dy1; const float* dy2; const float* y; int k;
   __device__ __forceinline__ float operator()(int, int co, int kk) const {
     long long o = (long long)kk * k + co;
-    return (__ldg(y + o) > 0.f) ? __ldg(dy + o) : 0.f;
+    return (__ldg(y + o) > 0.f) ? dy_sum(dy, dy1, dy2, o) : 0.f;
   }
 };
 // B(kk=(b,t), n=(tau,ci)) = xpad[b, t+tau-pad, ci]
@@ -72,10 +85,10 @@ struct StoreDW {
 };
 struct DpreCols {
   static constexpr bool fast_second = true;
-  const float* dy; const float* y; int k;
+  const float* dy; const float* dy1; const float* dy2; const float* y; int k;
   __device__ __forceinline__ float operator()(int, int m, int c) const {
     long long o = (long long)m * k + c;
-    return (__ldg(y + o) > 0.f) ? __ldg(dy + o) : 0.f;
+    return (__ldg(y + o) > 0.f) ? dy_sum(dy, dy1, dy2, o) : 0.f;
   }
 };
 
@@ -96,7 +109,11 @@ template <bool MASKED> struct OpA<ConvShiftLoad<MASKED>> {
       if (k0 + j < kend && ts >= 0 && ts < f.n) {
         long long o = ((long long)c.b * f.n + ts) * f.k + ch;
         val = __ldg(f.src + o);
-        if (MASKED) val = (__ldg(f.y + o) > 0.f) ? val : 0.f;
+        if (MASKED) {
+          if (f.src1) val += __ldg(f.src1 + o);
+          if (f.src2) val += __ldg(f.src2 + o);
+          val = (__ldg(f.y + o) > 0.f) ? val : 0.f;
+        }
       }
       v[j] = val;
       if (++ch == f.k) { ch = 0; ++tau; }
@@ -134,7 +151,7 @@ template <> struct OpA<DpreT> {         // A(m=co, kk=(b,t)) = dy * (y>0)
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       long long o = (long long)(k0 + j) * f.k + c.co;
-      v[j] = (k0 + j < kend && __ldg(f.y + o) > 0.f) ? __ldg(f.dy + o) : 0.f;
+      v[j] = (k0 + j < kend && __ldg(f.y + o) > 0.f) ? dy_sum(f.dy, f.dy1, f.dy2, o) : 0.f;
     }
   }
 };
@@ -158,7 +175,7 @@ extern "C" int mtadgat_conv_relu_fwd(const float* x, const float* w, const float
   MG_CHECK_ARG(x && w && bias && y, "conv_relu_fwd: null pointer");
   MG_CHECK_ARG(B > 0 && n > 0 && k > 0 && ks > 0 && (ks & 1), "conv_relu_fwd: need B,n,k>0 and odd kernel_size (got %d)", ks);
   cudaStream_t s = (cudaStream_t)stream;
-  ConvShiftLoad<false> A{x, nullptr, n, k, (ks - 1) / 2, +1};
+  ConvShiftLoad<false> A{x, nullptr, n, k, (ks - 1) / 2, +1, nullptr, nullptr};
   ConvWFwd Bw{w, k, ks};
   StStrided C{y, 0, k, 1, bias, ACT_RELU, 0};
   launch_gemm_batched(1, B * n, k, ks * k, A, Bw, C, s);
@@ -166,15 +183,16 @@ extern "C" int mtadgat_conv_relu_fwd(const float* x, const float* w, const float
   return MTADGAT_OK;
 }
 
-extern "C" int mtadgat_conv_relu_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx,
-                                     float* dw, float* db, int B, int n, int k, int ks, void* stream) {
+extern "C" int mtadgat_conv_relu_bwd3(const float* x, const float* w, const float* y, const float* dy, const float* dy1,
+                                      const float* dy2, float* dx, float* dw, float* db, int B, int n, int k, int ks,
+                                      void* stream) {
   MG_CHECK_ARG(x && w && y && dy && dw && db, "conv_relu_bwd: null pointer");
   MG_CHECK_ARG(B > 0 && n > 0 && k > 0 && ks > 0 && (ks & 1), "conv_relu_bwd: bad shape");
   cudaStream_t s = (cudaStream_t)stream;
   const int pad = (ks - 1) / 2;
   if (dx) {
     // dx[b,t',ci] = sum_{tau,co} dpre[b, t'-tau+pad, co] * w[co,ci,tau]
-    ConvShiftLoad<true> A{dy, y, n, k, pad, -1};
+    ConvShiftLoad<true> A{dy, y, n, k, pad, -1, dy1, dy2};
     ConvWBwd Bw{w, k, ks};
     StStrided C{dx, 0, k, 1, nullptr, ACT_NONE, 0};
     launch_gemm_batched(1, B * n, k, ks * k, A, Bw, C, s);
@@ -182,12 +200,17 @@ extern "C" int mtadgat_conv_relu_bwd(const float* x, const float* w, const float
   MG_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * k * ks, s));
   MG_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * (size_t)k, s));
   {
-    DpreT A{dy, y, k};
+    DpreT A{dy, dy1, dy2, y, k};
     ConvXCols Bx{x, n, k, pad};
     StoreDW C{dw, k, ks};
     launch_gemm_splitk(k, ks * k, B * n, A, Bx, C, s);
   }
-  launch_colsum(B * n, k, DpreCols{dy, y, k}, db, s);
+  launch_colsum(B * n, k, DpreCols{dy, dy1, dy2, y, k}, db, s);
   MG_CHECK_LAUNCH("conv_relu_bwd");
   return MTADGAT_OK;
+}
+
+extern "C" int mtadgat_conv_relu_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx,
+                                     float* dw, float* db, int B, int n, int k, int ks, void* stream) {
+  return mtadgat_conv_relu_bwd3(x, w, y, dy, nullptr, nullptr, dx, dw, db, B, n, k, ks, stream);
 }

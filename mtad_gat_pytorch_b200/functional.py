@@ -115,28 +115,42 @@ def _run_bwd(device, call, tensors):
 
 
 class ConvReluFn(torch.autograd.Function):
+    """y = relu(conv1d(x)).  With fanout > 1 the same result is returned `fanout` times (aliases of one buffer), one per
+    consumer, and the consumers' gradients are summed inside the backward kernels instead of by autograd add kernels."""
+
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, fanout=1):
         x, w, b = _prep(x, "x"), _prep(w, "conv weight"), _prep(b, "conv bias")
         B, n, k = x.shape
         ks = w.shape[2]
         y = torch.empty_like(x)
         check(lib.mtadgat_conv_relu_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), B, n, k, ks, _stream()))
         ctx.save_for_backward(x, w, y)
-        return y
+        if fanout == 1:
+            return y
+        return (y,) + tuple(y.view_as(y) for _ in range(fanout - 1))
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, *dys):
         x, w, y = ctx.saved_tensors
-        dy = _prep(dy, "dy")
+        dys = [_prep(d, "dy") for d in dys if d is not None]
+        if not dys:
+            return None, None, None, None
+        while len(dys) > 3:                       # the kernels take up to three sources
+            dys = [dys[0] + dys[1]] + dys[2:]
+        cur = torch.cuda.current_stream(x.device)
+        for d in dys:
+            d.record_stream(cur)
         B, n, k = x.shape
         ks = w.shape[2]
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dw = torch.empty_like(w)
         db = torch.empty(k, dtype=torch.float32, device=x.device)
-        check(lib.mtadgat_conv_relu_bwd(x.data_ptr(), w.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dx),
-                                        dw.data_ptr(), db.data_ptr(), B, n, k, ks, _stream()))
-        return dx, dw, db
+        check(lib.mtadgat_conv_relu_bwd3(x.data_ptr(), w.data_ptr(), y.data_ptr(), dys[0].data_ptr(),
+                                         dys[1].data_ptr() if len(dys) > 1 else None,
+                                         dys[2].data_ptr() if len(dys) > 2 else None, _ptr(dx),
+                                         dw.data_ptr(), db.data_ptr(), B, n, k, ks, _stream()))
+        return dx, dw, db, None
 
 
 class GatFn(torch.autograd.Function):

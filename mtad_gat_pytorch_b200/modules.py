@@ -35,6 +35,11 @@ class ConvLayer(nn.Module):
     def forward(self, x):
         return F.ConvReluFn.apply(x, self.conv.weight, self.conv.bias)
 
+    def forward_fanout(self, x, fanout):
+        """The same output `fanout` times (aliases), one per consumer: their gradients are summed inside the
+        backward kernels (used by MTAD_GAT.forward, whose conv output feeds both GAT layers and the GRU)."""
+        return F.ConvReluFn.apply(x, self.conv.weight, self.conv.bias, fanout)
+
 
 class _GraphAttention(nn.Module, _SeedMixin):
     """Shared body of the feature- and time-oriented GAT layers (reference modules.py:25-217)."""

@@ -46,14 +46,15 @@ class MTAD_GAT(nn.Module):
         for m in self._seeded():
             m._step_seed = seed
         try:
-            xc = self.conv(x)                                   # mtad_gat.py:67
+            # mtad_gat.py:67 -- one result, three handles (GRU slice, feature GAT, temporal GAT): see ConvReluFn
+            xc, xc_f, xc_t = self.conv.forward_fanout(x, 3)
             if self.branch_parallel:
                 main, side = torch.cuda.current_stream(x.device), self._side_stream(x.device)
                 side.wait_stream(main)
                 xc.record_stream(side)
                 with torch.cuda.stream(side):
-                    h_feat = self.feature_gat(xc)               # :68
-                h_temp = self.temporal_gat(xc)                  # :69
+                    h_feat = self.feature_gat(xc_f)             # :68
+                h_temp = self.temporal_gat(xc_t)                # :69
                 main.wait_stream(side)
                 h_feat.record_stream(main)
                 h_end = self.gru.forward_slices([xc, h_feat, h_temp])   # :71-74 (cat never materialised)
@@ -65,8 +66,8 @@ class MTAD_GAT(nn.Module):
                 main.wait_stream(side)
                 predictions.record_stream(main)
             else:
-                h_feat = self.feature_gat(xc)
-                h_temp = self.temporal_gat(xc)
+                h_feat = self.feature_gat(xc_f)
+                h_temp = self.temporal_gat(xc_t)
                 h_end = self.gru.forward_slices([xc, h_feat, h_temp])
                 predictions = self.forecasting_model(h_end)
                 recons = self.recon_model(h_end)
