@@ -44,14 +44,9 @@ __device__ __forceinline__ void pack_row(const F& f, int z, int L, int K, int lt
       Op::load8(f, ctx, z, ktile * BK + g * 8, K, v);
       tcg::store_split8(hi, lo, (uint32_t)(g * R + row) * 16, v);
     }
-  } else {
-    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-    for (int g = 0; g < KG; ++g) {
-      *reinterpret_cast<uint4*>(hi + (size_t)(g * R + row) * 16) = zero;
-      *reinterpret_cast<uint4*>(lo + (size_t)(g * R + row) * 16) = zero;
-    }
   }
+  // rows beyond the operand's last line are never written: gemm2_kernel copies only the live rows of a partial tile
+  // and keeps the rest of its shared-memory stage at zero
 }
 
 // one thread per (z, line tile, k tile, row): 32 consecutive K of one operand line -> 4 hi + 4 lo 16-byte groups.
@@ -114,6 +109,13 @@ __global__ void __launch_bounds__(NTHREADS) gemm2_kernel(const uint8_t* __restri
     tc::mbar_init(accb, 1);
     tc::fence_mbar_init();
   }
+  // partial tiles (last m / n tile): only the live rows are copied per k-tile, the dead rows of every stage stay zero
+  const int rowsA = min(BM, M - m0), rowsB = min(BN, N - n0);
+  if (rowsA < BM || rowsB < BN) {
+    for (int idx = tid; idx < STAGES * S::STAGE / 16; idx += NTHREADS)
+      reinterpret_cast<uint4*>(smem_raw)[idx] = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_proxy_async_smem();           // generic-proxy zeros must be visible to the MMAs' async-proxy reads
+  }
   if (warp == 0) tc::tmem_alloc(slot, BN);
   tc::tc_fence_before();
   __syncthreads();
@@ -129,10 +131,18 @@ __global__ void __launch_bounds__(NTHREADS) gemm2_kernel(const uint8_t* __restri
       for (int i = 0; i < nkt; ++i) {
         const int s = i % STAGES;
         if (i >= STAGES) tc::mbar_wait(empty + s, ((i / STAGES) - 1) & 1);
-        arrive_expect_tx(full + s, (uint32_t)S::STAGE);
-        bulk_g2s(sbase + (uint32_t)(s * S::STAGE), a_src + (size_t)i * Tile<BM>::BYTES, Tile<BM>::BYTES, full + s);
-        bulk_g2s(sbase + (uint32_t)(s * S::STAGE) + Tile<BM>::BYTES, b_src + (size_t)i * Tile<BN>::BYTES, Tile<BN>::BYTES,
-                 full + s);
+        arrive_expect_tx(full + s, (uint32_t)(2 * KG * 16 * (rowsA + rowsB)));
+        const uint32_t sa = sbase + (uint32_t)(s * S::STAGE), sb = sa + Tile<BM>::BYTES;
+        const uint8_t* ga = a_src + (size_t)i * Tile<BM>::BYTES;
+        const uint8_t* gb = b_src + (size_t)i * Tile<BN>::BYTES;
+        if (rowsA == BM) bulk_g2s(sa, ga, Tile<BM>::BYTES, full + s);
+        else
+          for (int g = 0; g < 2 * KG; ++g)        // one copy per (hi|lo, k group): the live rows are contiguous there
+            bulk_g2s(sa + (uint32_t)(g * BM * 16), ga + (size_t)g * BM * 16, (uint32_t)rowsA * 16, full + s);
+        if (rowsB == BN) bulk_g2s(sb, gb, Tile<BN>::BYTES, full + s);
+        else
+          for (int g = 0; g < 2 * KG; ++g)
+            bulk_g2s(sb + (uint32_t)(g * BN * 16), gb + (size_t)g * BN * 16, (uint32_t)rowsB * 16, full + s);
       }
     }
   } else if (warp == 1) {
