@@ -213,15 +213,6 @@ struct DpqB {
     return __ldg(dpqt + ((long long)b * NC + c) * Kp + node);
   }
 };
-// dbp[c] = sum_{b,node} dPQt[b][c][node]
-struct DpqCols {
-  static constexpr bool fast_second = false;
-  const float* dpqt; int NC, Kp, K;
-  __device__ __forceinline__ float operator()(int, int m, int c) const {
-    int b = m / K, node = m - b * K;
-    return __ldg(dpqt + ((long long)b * NC + c) * Kp + node);
-  }
-};
 // dV(b,node,dd) += sum_c dPQt[b][c][node] Wp[dd][c]    batched over b
 struct DpqA {
   static constexpr bool fast_second = false;     // m(node)-fast
@@ -389,7 +380,7 @@ struct ScoreParams {
 
 template <int MI, int MJ>
 __global__ void __launch_bounds__(256) gat_score_fwd_kernel(ScoreParams P) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int b = blockIdx.y, i0 = blockIdx.x * P.RB;
   const int rb = min(P.RB, P.K - i0);
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -580,7 +571,7 @@ struct Bwd1Params {
 
 template <int MI>
 __global__ void __launch_bounds__(256) gat_bwd1_kernel(Bwd1Params P) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int b = blockIdx.y, i0 = blockIdx.x * P.RB;
   const int rb = min(P.RB, P.K - i0);
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -735,7 +726,7 @@ struct Bwd2Params {
 // load of w (4 rows) and one of Y (4 channels, Y staged column-major [c][DTp]) feed 16 compare-and-add pairs, so the
 // loop is bound by FP issue rather than shared-memory wavefronts.
 __global__ void __launch_bounds__(256) gat_bwd2_kernel(Bwd2Params P) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int b = blockIdx.z, d0 = blockIdx.x * P.DT, r0 = blockIdx.y * P.RBk;
   const int K = P.K, Kp = P.Kp, E = P.E, RBk = P.RBk;
   const int rbk = min(RBk, Kp - r0);          // rows handled here (multiple of 4; rows >= K are padding)
@@ -837,7 +828,7 @@ __global__ void __launch_bounds__(256) gat_bwd2_kernel(Bwd2Params P) {
 // Thread item = (row r, 16 channels): per column c one scalar w load, four vector Y loads, 16 compare-and-adds.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) gat_bwd2_win_kernel(Bwd2Params P) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   const int b = blockIdx.x;
   const int K = P.K, Kp = P.Kp, E = P.E;
   const int tid = threadIdx.x;

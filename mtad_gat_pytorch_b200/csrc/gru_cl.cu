@@ -43,9 +43,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint32_t x, uint32_t y) {
-  asm volatile("st.shared::cluster.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
-}
 // asynchronous 8-byte store into a (possibly remote) CTA's shared memory that completes `8` tx-bytes on that CTA's
 // mbarrier: data hand-off and signalling in one instruction, no fences or release-arrives on the producer side
 __device__ __forceinline__ void st_async_v2(uint32_t dst_cluster_addr, uint32_t x, uint32_t y, uint32_t mbar_cluster_addr) {
@@ -57,34 +54,8 @@ __device__ __forceinline__ void st_async_v4(uint32_t dst_cluster_addr, uint32_t 
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
                ::"r"(dst_cluster_addr), "r"(x), "r"(y), "r"(z), "r"(w), "r"(mbar_cluster_addr) : "memory");
 }
-// bulk copy of a contiguous chunk of this CTA's shared memory into a peer CTA's shared memory; completes `bytes`
-// tx-bytes on the peer's mbarrier (ONE barrier update per copy instead of one per 8-byte store)
-__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
-                                                  uint32_t mbar_cluster_addr) {
-  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t tx_bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(tx_bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(tc::smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  for (uint32_t it = 0; it < (1u << 26); ++it)
-    if (mbar_try_wait_cluster(bar, parity)) return;
-  __trap();
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
