@@ -203,9 +203,10 @@ extern "C" int mtadgat_conv_relu_bwd3(const float* x, const float* w, const floa
     DpreT A{dy, dy1, dy2, y, k};
     ConvXCols Bx{x, n, k, pad};
     StoreDW C{dw, k, ks};
-    launch_gemm_splitk(k, ks * k, B * n, A, Bx, C, s);
+    // db[co] = sum_kk A(co, kk): accumulated by the operand pack when the packed GEMM runs
+    if (!launch_gemm_splitk(k, ks * k, B * n, A, Bx, C, s, 592, db, nullptr))
+      launch_colsum(B * n, k, DpreCols{dy, dy1, dy2, y, k}, db, s);
   }
-  launch_colsum(B * n, k, DpreCols{dy, dy1, dy2, y, k}, db, s);
   MG_CHECK_LAUNCH("conv_relu_bwd");
   return MTADGAT_OK;
 }

@@ -1320,9 +1320,11 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
   if (do_par) {
     DpqB Bq{dpqt, d.NC, d.Kp, d.K};
     StAtomic2 C{dwp, d.NC};
-    if (feature) launch_gemm_splitk(d.D, d.NC, B * d.K, NodeAT<true>{x, n, k, d.K}, Bq, C, s);
-    else launch_gemm_splitk(d.D, d.NC, B * d.K, NodeAT<false>{x, n, k, d.K}, Bq, C, s);
-    {
+    // dbp[c] = sum_kk B(kk, c): accumulated by the operand pack when the packed GEMM runs
+    bool sums;
+    if (feature) sums = launch_gemm_splitk(d.D, d.NC, B * d.K, NodeAT<true>{x, n, k, d.K}, Bq, C, s, 592, nullptr, dbp);
+    else sums = launch_gemm_splitk(d.D, d.NC, B * d.K, NodeAT<false>{x, n, k, d.K}, Bq, C, s, 592, nullptr, dbp);
+    if (!sums) {
       const int nsplit = max(1, min(cdiv(B, 8), cdiv(592, d.NC))), bper = cdiv(B, nsplit);
       dpq_colsum_kernel<<<dim3(d.NC, cdiv(B, bper)), 256, 0, s>>>(dpqt, B, d.NC, d.K, d.Kp, bper, dbp);
       MG_COUNT_LAUNCH();

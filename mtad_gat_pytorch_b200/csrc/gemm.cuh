@@ -149,11 +149,14 @@ static inline void launch_gemm_batched(int batch, int M, int N, int K, AL A, BL 
 }
 
 // Split-K: C must be zero-initialised by the caller (cudaMemsetAsync); bias/act are ignored.
+// sumA / sumB (nullable, zero-initialised by the caller): sumA[m] += sum_k A(m,k), sumB[n] += sum_k B(k,n).  Returns true
+// when the sums were produced (packed-operand path); false = the caller must run its own column-sum kernel.
 template <class AL, class BL, class CS>
-static inline void launch_gemm_splitk(int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s, int target_ctas = 592) {
-  if (M <= 0 || N <= 0) return;
-  if (g_mtadgat_gemm_impl == 1 && M >= 32 && N >= 16) { tcg2::launch_splitk(M, N, K, A, Bm, C, s, 296); return; }
-  if (g_mtadgat_gemm_impl == 2 && M >= 32 && N >= 16) { tcg::launch_splitk(M, N, K, A, Bm, C, s, 296); return; }
+static inline bool launch_gemm_splitk(int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s, int target_ctas = 592,
+                                      float* sumA = nullptr, float* sumB = nullptr) {
+  if (M <= 0 || N <= 0) return false;
+  if (g_mtadgat_gemm_impl == 1 && M >= 32 && N >= 16) { tcg2::launch_splitk(M, N, K, A, Bm, C, s, 296, sumA, sumB); return true; }
+  if (g_mtadgat_gemm_impl == 2 && M >= 32 && N >= 16) { tcg::launch_splitk(M, N, K, A, Bm, C, s, 296); return false; }
   int tiles = cdiv(N, GEMM_BN) * cdiv(M, GEMM_BM);
   int splits = max(1, min(cdiv(K, 4 * GEMM_BK), cdiv(target_ctas, tiles)));
   int klen = cdiv(cdiv(K, splits), GEMM_BK) * GEMM_BK;
@@ -161,6 +164,7 @@ static inline void launch_gemm_splitk(int M, int N, int K, AL A, BL Bm, CS C, cu
   dim3 g(cdiv(N, GEMM_BN), cdiv(M, GEMM_BM), splits);
   gemm_kernel<AL, BL, CS><<<g, 256, 0, s>>>(M, N, K, klen, 1, A, Bm, C);
   MG_COUNT_LAUNCH();
+  return false;
 }
 
 // out[n] += sum_m A(0,m,n)   (out zero-initialised by the caller); A should be n-fast for coalescing.

@@ -661,11 +661,17 @@ extern "C" int mtadgat_gru_bwd(const float* x0, const float* x1, const float* x2
     MG_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * (size_t)G * H, s));
     MG_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)G, s));
     MG_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)G, s));
-    launch_gemm_splitk(G, I, Rt, TiledT{dgi, G}, Cat3BT{x0, x1, x2, k0, k1, k2, n, B}, StAtomic2{dw_ih, I}, s);
-    launch_gemm_splitk(G, H, Rt, DghTT{dgi, dghn, H}, HprevBT{out, n, H, B}, StAtomic2{dw_hh, H}, s);
-    launch_colsum_tiled(dgi, Rt / 16, G, db_ih, s);
-    launch_colsum_tiled(dghn, Rt / 16, H, db_hh + 2 * H, s);
-    MG_CUDA(cudaMemcpyAsync(db_hh, db_ih, sizeof(float) * (size_t)2 * H, cudaMemcpyDeviceToDevice, s));
+    // db_ih = line sums of the dW_ih operand (dgi), db_hh = line sums of the dW_hh operand ([dpr; dpz; dgh_n]):
+    // accumulated by the operand packs when the packed GEMM runs
+    const bool s1 = launch_gemm_splitk(G, I, Rt, TiledT{dgi, G}, Cat3BT{x0, x1, x2, k0, k1, k2, n, B}, StAtomic2{dw_ih, I}, s,
+                                       592, db_ih, nullptr);
+    const bool s2 = launch_gemm_splitk(G, H, Rt, DghTT{dgi, dghn, H}, HprevBT{out, n, H, B}, StAtomic2{dw_hh, H}, s, 592,
+                                       db_hh, nullptr);
+    if (!s1) launch_colsum_tiled(dgi, Rt / 16, G, db_ih, s);
+    if (!s2) {
+      launch_colsum_tiled(dghn, Rt / 16, H, db_hh + 2 * H, s);
+      MG_CUDA(cudaMemcpyAsync(db_hh, db_ih, sizeof(float) * (size_t)2 * H, cudaMemcpyDeviceToDevice, s));
+    }
   }
   if ((parts & 1) && (dx0 || dx1 || dx2)) {
     // dx = dgi W_ih : A(m=r,kk=g) = dgi_t[r][g] ; B(kk=g, n=i) = w_ih[g, i]
@@ -735,10 +741,13 @@ extern "C" int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const 
     MG_CUDA(cudaMemsetAsync(dw_hh, 0, sizeof(float) * (size_t)G * R, s));
     MG_CUDA(cudaMemsetAsync(db_ih, 0, sizeof(float) * (size_t)G, s));
     MG_CUDA(cudaMemsetAsync(db_hh, 0, sizeof(float) * (size_t)G, s));
-    launch_gemm_splitk(G, R, Rt, DghTT{dgi, dghn, R}, HprevBT{out, n, R, B}, StAtomic2{dw_hh, R}, s);
+    const bool s2 = launch_gemm_splitk(G, R, Rt, DghTT{dgi, dghn, R}, HprevBT{out, n, R, B}, StAtomic2{dw_hh, R}, s, 592,
+                                       db_hh, nullptr);
     launch_colsum_tiled(dgi, Rt / 16, G, db_ih, s);
-    launch_colsum_tiled(dghn, Rt / 16, R, db_hh + 2 * R, s);
-    MG_CUDA(cudaMemcpyAsync(db_hh, db_ih, sizeof(float) * (size_t)2 * R, cudaMemcpyDeviceToDevice, s));
+    if (!s2) {
+      launch_colsum_tiled(dghn, Rt / 16, R, db_hh + 2 * R, s);
+      MG_CUDA(cudaMemcpyAsync(db_hh, db_ih, sizeof(float) * (size_t)2 * R, cudaMemcpyDeviceToDevice, s));
+    }
     rep_dS_kernel<<<cdiv((long long)n * J * G, 256), 256, 0, s>>>(dgi, h_src, B, n, Hs, G, J, dS);
     MG_COUNT_LAUNCH();
     rep_dw_kernel<<<cdiv((long long)G * Hs, 256), 256, 0, s>>>(dS, n, Hs, G, J, dw_ih);

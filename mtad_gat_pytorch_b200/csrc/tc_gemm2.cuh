@@ -31,19 +31,25 @@ template <class C> struct NFast { static constexpr bool value = true; };
 // functors whose value does not depend on the batch index z are packed once (specialise to true)
 template <class F> struct BatchInvariant { static constexpr bool value = false; };
 
+// linesum (nullable): linesum[l] += sum_k operand(l, k) -- the bias gradients of the path are exactly the line sums of a
+// weight-gradient GEMM operand, so they ride along with the pack instead of costing a column-sum kernel
 template <class Op, class F, int R>
-__device__ __forceinline__ void pack_row(const F& f, int z, int L, int K, int ltile, int ktile, int row, uint8_t* tile) {
+__device__ __forceinline__ void pack_row(const F& f, int z, int L, int K, int ltile, int ktile, int row, uint8_t* tile,
+                                         float* __restrict__ linesum) {
   const int l = ltile * R + row;
   uint8_t* hi = tile;
   uint8_t* lo = tile + Tile<R>::HALF;
   if (l < L) {
     const typename Op::Ctx ctx = Op::line(f, z, l);
+    float acc = 0.f;
 #pragma unroll
     for (int g = 0; g < KG; ++g) {
       float v[8];
       Op::load8(f, ctx, z, ktile * BK + g * 8, K, v);
       tcg::store_split8(hi, lo, (uint32_t)(g * R + row) * 16, v);
+      acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     }
+    if (linesum) atomicAdd(linesum + l, acc);
   }
   // rows beyond the operand's last line are never written: gemm2_kernel copies only the live rows of a partial tile
   // and keeps the rest of its shared-memory stage at zero
@@ -53,7 +59,8 @@ __device__ __forceinline__ void pack_row(const F& f, int z, int L, int K, int lt
 // Threads [0, nA) pack A, the rest pack B (both counts are multiples of 32: warps never straddle).
 template <class AL, class BL, int BN>
 __global__ void __launch_bounds__(256) pack_kernel(AL A, BL Bm, int M, int N, int K, int KT, int MT, int NT, int nzA,
-                                                   int nzB, uint8_t* __restrict__ Ap, uint8_t* __restrict__ Bp) {
+                                                   int nzB, uint8_t* __restrict__ Ap, uint8_t* __restrict__ Bp,
+                                                   float* __restrict__ sumA, float* __restrict__ sumB) {
   long long g = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long nA = (long long)nzA * MT * KT * BM, nB = (long long)nzB * NT * KT * BN;
   if (g < nA) {
@@ -61,14 +68,14 @@ __global__ void __launch_bounds__(256) pack_kernel(AL A, BL Bm, int M, int N, in
     long long tile = g / BM;
     const int ktile = (int)(tile % KT);
     const long long t2 = tile / KT;
-    pack_row<tcg::OpA<AL>, AL, BM>(A, (int)(t2 / MT), M, K, (int)(t2 % MT), ktile, row, Ap + tile * Tile<BM>::BYTES);
+    pack_row<tcg::OpA<AL>, AL, BM>(A, (int)(t2 / MT), M, K, (int)(t2 % MT), ktile, row, Ap + tile * Tile<BM>::BYTES, sumA);
   } else if (g - nA < nB) {
     g -= nA;
     const int row = (int)(g % BN);
     long long tile = g / BN;
     const int ktile = (int)(tile % KT);
     const long long t2 = tile / KT;
-    pack_row<tcg::OpB<BL>, BL, BN>(Bm, (int)(t2 / NT), N, K, (int)(t2 % NT), ktile, row, Bp + tile * Tile<BN>::BYTES);
+    pack_row<tcg::OpB<BL>, BL, BN>(Bm, (int)(t2 / NT), N, K, (int)(t2 % NT), ktile, row, Bp + tile * Tile<BN>::BYTES, sumB);
   }
 }
 
@@ -221,7 +228,8 @@ __global__ void __launch_bounds__(NTHREADS) gemm2_kernel(const uint8_t* __restri
 }
 
 template <class AL, class BL, class CS, int BN>
-static inline int run(int batch, int M, int N, int K, int splits_wanted, bool splitk, AL A, BL Bm, CS C, cudaStream_t s) {
+static inline int run(int batch, int M, int N, int K, int splits_wanted, bool splitk, AL A, BL Bm, CS C, cudaStream_t s,
+                      float* sumA = nullptr, float* sumB = nullptr) {
   const int KT = cdiv(K, BK), MT = cdiv(M, BM), NT = cdiv(N, BN);
   const int nzA = (!splitk && !BatchInvariant<AL>::value) ? batch : 1;
   const int nzB = (!splitk && !BatchInvariant<BL>::value) ? batch : 1;
@@ -230,7 +238,7 @@ static inline int run(int batch, int M, int N, int K, int splits_wanted, bool sp
   if (!ws) { mtadgat_set_pending_error(MTADGAT_ERR_CUDA); return MTADGAT_ERR_CUDA; }
   uint8_t* Ap = ws; uint8_t* Bp = ws + a_bytes;
   const long long nthreads = (long long)nzA * MT * KT * BM + (long long)nzB * NT * KT * BN;
-  pack_kernel<AL, BL, BN><<<cdiv(nthreads, 256), 256, 0, s>>>(A, Bm, M, N, K, KT, MT, NT, nzA, nzB, Ap, Bp);
+  pack_kernel<AL, BL, BN><<<cdiv(nthreads, 256), 256, 0, s>>>(A, Bm, M, N, K, KT, MT, NT, nzA, nzB, Ap, Bp, sumA, sumB);
   MG_COUNT_LAUNCH();
   constexpr int smem = Smem2<BN>::TOTAL;
   static bool configured = false;
@@ -257,12 +265,13 @@ static inline int launch_batched(int batch, int M, int N, int K, AL A, BL Bm, CS
 }
 
 template <class AL, class BL, class CS>
-static inline int launch_splitk(int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s, int target_ctas) {
+static inline int launch_splitk(int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s, int target_ctas,
+                                float* sumA = nullptr, float* sumB = nullptr) {
   const int bn = N <= 64 ? 64 : 128;
   const int tiles = cdiv(N, bn) * cdiv(M, BM);
   const int splits = max(1, min(cdiv(K, 4 * BK), cdiv(target_ctas, tiles)));
-  if (bn == 64) return run<AL, BL, CS, 64>(1, M, N, K, splits, true, A, Bm, C, s);
-  return run<AL, BL, CS, 128>(1, M, N, K, splits, true, A, Bm, C, s);
+  if (bn == 64) return run<AL, BL, CS, 64>(1, M, N, K, splits, true, A, Bm, C, s, sumA, sumB);
+  return run<AL, BL, CS, 128>(1, M, N, K, splits, true, A, Bm, C, s, sumA, sumB);
 }
 
 }  // namespace tcg2
