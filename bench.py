@@ -234,8 +234,9 @@ def run_ours(args):
             if i > 0:
                 last = step.collect()
         last = step.collect()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / args.steps
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / args.steps     # local wall time; MAX over ranks below (the closing
+        barrier()                                           # collective barrier itself is not part of the K steps)
     t_ms = torch.tensor([ms_dev, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
