@@ -32,8 +32,11 @@ def allreduce_gradients(params, world_size):
         return
     grads = [p.grad for p in params]
     flat = torch._utils._flatten_dense_tensors(grads)
-    dist.all_reduce(flat)
-    flat.div_(world_size)
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)        # the average is formed inside the collective
+    else:
+        dist.all_reduce(flat)
+        flat.div_(world_size)
     torch._foreach_copy_(grads, torch._utils._unflatten_dense_tensors(flat, grads))
 
 
