@@ -132,7 +132,9 @@ int mtadgat_set_gemm_impl(int impl);
 int mtadgat_get_gemm_impl(void);
 /* The packed-operand GEMM keeps ONE grow-only device buffer per stream it is called on (the only memory the library
  * owns).  It grows on demand, except while the stream is being captured into a CUDA graph: run the same call eagerly
- * once on that stream first, or reserve it here.  _release frees every buffer (synchronises the device). */
+ * once on that stream first, or reserve it here.  A buffer that a capture has used is never freed when the workspace
+ * later grows (replays of that graph stay valid).  _release frees every buffer (synchronises the device; graphs
+ * captured before it must not be replayed afterwards). */
 int mtadgat_workspace_reserve(void* stream, long long bytes);
 void mtadgat_workspace_release(void);
 int mtadgat_tc_probe(const float* A, const float* Bm, float* D, int Mtot, int row0, int K, int N, int b_mn_major,

@@ -15,16 +15,22 @@ int mtadgat_take_pending_error(void) { int r = g_pending_rc; g_pending_rc = 0; r
 // ---- pack workspace: one grow-only device buffer per stream (kernels of one stream run in order, so a buffer is
 //      never rewritten while an earlier GEMM of the same stream still reads it) ----
 namespace {
-struct WsSlot { cudaStream_t s; uint8_t* p; size_t bytes; bool used; };
+struct WsSlot { cudaStream_t s; uint8_t* p; size_t bytes; bool used; bool captured; };
 WsSlot g_ws[32];
+uint8_t* g_retired[256];       // buffers that a captured CUDA graph may still reference: kept until workspace_release
+int g_nretired = 0;
 }
 uint8_t* mtadgat_workspace(cudaStream_t s, size_t bytes) {
   WsSlot* slot = nullptr;
   for (auto& w : g_ws) if (w.used && w.s == s) { slot = &w; break; }
-  if (slot && slot->bytes >= bytes) return slot->p;
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(s, &st);
-  if (st != cudaStreamCaptureStatusNone) {
+  const bool capturing = st != cudaStreamCaptureStatusNone;
+  if (slot && slot->bytes >= bytes) {
+    if (capturing) slot->captured = true;     // a graph now holds pointers into this buffer: it is never freed on growth
+    return slot->p;
+  }
+  if (capturing) {
     mtadgat_set_error("GEMM pack workspace of this stream is %zu bytes but %zu are needed, and it cannot grow while the "
                       "stream is being captured: run the step eagerly once on the same streams before capture, or call "
                       "mtadgat_workspace_reserve", slot ? slot->bytes : (size_t)0, bytes);
@@ -33,9 +39,19 @@ uint8_t* mtadgat_workspace(cudaStream_t s, size_t bytes) {
   if (!slot) {
     for (auto& w : g_ws) if (!w.used) { slot = &w; break; }
     if (!slot) { mtadgat_set_error("workspace: more than 32 distinct streams"); return nullptr; }
-    slot->used = true; slot->s = s; slot->p = nullptr; slot->bytes = 0;
+    slot->used = true; slot->s = s; slot->p = nullptr; slot->bytes = 0; slot->captured = false;
   }
-  if (slot->p) { cudaStreamSynchronize(s); cudaFree(slot->p); slot->p = nullptr; slot->bytes = 0; }
+  if (slot->p) {
+    if (slot->captured) {
+      // a captured graph may replay with pointers into the old buffer: retire it instead of freeing it
+      if (g_nretired == 256) { mtadgat_set_error("workspace: too many buffers retired by graph captures"); return nullptr; }
+      g_retired[g_nretired++] = slot->p;
+    } else {
+      cudaStreamSynchronize(s);
+      cudaFree(slot->p);
+    }
+    slot->p = nullptr; slot->bytes = 0; slot->captured = false;
+  }
   size_t want = bytes + bytes / 4 + (1u << 20);
   cudaError_t e = cudaMalloc(&slot->p, want);
   if (e != cudaSuccess) {
@@ -54,6 +70,8 @@ extern "C" int mtadgat_workspace_reserve(void* stream, long long bytes) {
 extern "C" void mtadgat_workspace_release(void) {
   cudaDeviceSynchronize();
   for (auto& w : g_ws) if (w.used) { if (w.p) cudaFree(w.p); w = WsSlot{}; }
+  for (int i = 0; i < g_nretired; ++i) cudaFree(g_retired[i]);
+  g_nretired = 0;
 }
 
 void mtadgat_set_error(const char* fmt, ...) {

@@ -494,3 +494,25 @@ def test_pack_workspace_cannot_grow_during_capture():
         out = lin(x)
     g2.replay(); torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+def test_pack_workspace_growth_keeps_captured_graphs_valid():
+    """A workspace buffer that a capture has used is retired, not freed, when a later (larger) eager call on the same
+    stream makes the workspace grow: replaying the graph afterwards still gives the captured result."""
+    import mtad_gat_pytorch_b200 as mg
+    lin = mg.Forecasting_Model(64, 64, 64, 1, 0.0).cuda().eval()
+    x = torch.rand(300, 64, device="cuda")
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ref = lin(x)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        out = lin(x)
+    big = torch.rand(200000, 64, device="cuda")
+    with torch.cuda.stream(s):
+        lin(big)                                   # forces the stream's workspace to grow
+    torch.cuda.synchronize()
+    out.zero_()
+    g.replay(); torch.cuda.synchronize()
+    assert torch.equal(out, ref)
