@@ -1,19 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- windows/sec of the MTAD-GAT training step (forward + loss + backward + Adam) at SMD shape.
+"""bench.py -- windows/sec of the MTAD-GAT hot path on B200, next to the reference's own PyTorch path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-graph] [--batch B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c3|c4|c5]
+                    [--scaling weak|strong] [--gatv1] [--batch B] [--no-graph] [--skip-cpu] [--skip-ref-cuda]
 
-Workload (BASELINE.json configs[1]): MTAD_GAT(k=38, n=100, out=38, forecast_n_layers=3, dropout=0.3) in train
-mode, batch 256 windows per GPU of synthetic uniform[0,1) data, loss = sqrt(mse)+sqrt(mse) as training.py:122-124,
-torch.optim.Adam(lr=1e-3).  One "step" = one pass of the hot path over one batch, optimizer step included.
+Default workload (BASELINE.json configs[1], "C2"): MTAD_GAT(k=38, n=100, out=38, forecast_n_layers=3, dropout=0.3) in
+train mode, 256 windows per GPU of synthetic uniform[0,1) data; one step = zero_grad, forward, sqrt(mse)+sqrt(mse)
+loss, backward, Adam (the reference's training.py:109-127).  Other BASELINE.json configs: --config c3 (k=55, out=1,
+forward-only scoring, batch 4096), c4 (k=512, batch 1024 GLOBAL, strong scaling), c5 (n=512, batch 512 global).
 
-JSON line keys follow the driver contract: value (device-resident inputs, CUDA-event timed, L2 flushed between
-steps), e2e (host pinned inputs -> H2D -> step -> D2H loss, wall clock), roofline (per-kernel, measured live with
-CUDA events), cpu_baseline (the numpy oracle port timed on a bounded sample on the host cores), clocks.
-`--impl reference` times the CPU port of the reference path (oracle/) instead -- the reference is Python/torch
-and cannot travel to the GPU box, see DESIGN.md.
+JSON line (driver contract): value = device-resident inputs, per-step CUDA events, L2 flushed between steps;
+e2e = pinned host batch -> H2D -> step -> D2H result inside the timed region; roofline = the dominant single kernel,
+timed live, against SURVEY section 8(d) algorithmic bytes; cpu_baseline = the UNMODIFIED reference (baseline/_ref, staged by
+__graft_entry__.build() from /root/reference) on the host cores; reference_cuda = the same reference model run eagerly
+on this GPU (cuBLAS/cuDNN: what a user of the reference gets today; informative).
+`--impl reference` runs only that reference on the host CPU at the same config (same batch for C2).
 """
 import argparse
+import csv
+import glob
+import importlib
 import json
 import os
 import subprocess
@@ -25,64 +31,196 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
-K_FEAT, N_WIN, OUT_DIM, BATCH = 38, 100, 38, 256
-MODEL_KW = dict(n_features=K_FEAT, window_size=N_WIN, out_dim=OUT_DIM, forecast_n_layers=3, dropout=0.3)
-WORKLOAD = "SMD-shape (k=38,n=100) MTAD_GAT train step fwd+bwd+Adam, batch 256/GPU, fp32"
+# name -> model kwargs, mode, batch as BASELINE.json states it, whether that batch is global, reference micro-batch
+CONFIGS = {
+    "c2": dict(kw=dict(n_features=38, window_size=100, out_dim=38, forecast_n_layers=3, dropout=0.3), train=True,
+               batch=256, batch_is_global=False, ref_batch=256,
+               label="SMD-shape (k=38,n=100) MTAD_GAT train step fwd+bwd+Adam, batch 256/GPU, fp32"),
+    "c3": dict(kw=dict(n_features=55, window_size=100, out_dim=1, forecast_n_layers=3, dropout=0.3), train=False,
+               batch=4096, batch_is_global=False, ref_batch=256,
+               label="MSL-shape (k=55,n=100,out=1) MTAD_GAT forward-only scoring, batch 4096/GPU, fp32"),
+    "c4": dict(kw=dict(n_features=512, window_size=100, out_dim=512, forecast_n_layers=3, dropout=0.3), train=True,
+               batch=1024, batch_is_global=True, ref_batch=4,
+               label="wide-feature (k=512,n=100) MTAD_GAT train step, global batch 1024, fp32"),
+    "c5": dict(kw=dict(n_features=38, window_size=512, out_dim=38, forecast_n_layers=3, dropout=0.3), train=True,
+               batch=512, batch_is_global=True, ref_batch=8,
+               label="long-window (k=38,n=512) MTAD_GAT train step, global batch 512, fp32"),
+}
+METRIC = "windows/sec MTAD-GAT fwd+bwd (k=38,n=100)"
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch at the default workload, from the `ncu --set full` capture
-# summarised in profiles/ (cold caches: ncu flushes L2 before every replay pass)
-NCU_TRAFFIC = {"gru_recurrence_bwd_kernel": 108.3e6, "gru_recurrence_fwd_kernel": 73.3e6}   # profiles/r1_final_gru_cl_raw.csv
+def metric_name(cfgname):
+    c = CONFIGS[cfgname]
+    k, n = c["kw"]["n_features"], c["kw"]["window_size"]
+    return METRIC if cfgname == "c2" else f"windows/sec MTAD-GAT {'fwd+bwd' if c['train'] else 'fwd'} (k={k},n={n})"
 
 
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
-    return {"hbm_gbs": 6650.0, "bf16_tflops": 1400.0, "src": "fallback"}
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "MEASURED_PEAKS.json"}
+    # fallback stated in /opt/skills/guides/B200_PROFILING.md
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1700.0, "bf16_tflops_sustained": 1400.0, "src": "B200_PROFILING.md fallback"}
+
+
+def ncu_traffic(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the newest
+    profiles/*traffic*.csv (written by scripts/ncu_traffic.py from an `ncu --set full` capture of this command).
+    None when no capture names the kernel: the number is never a constant in this file."""
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*traffic*.csv"))):
+        try:
+            for row in csv.DictReader(open(path)):
+                if kernel_substr in row.get("kernel", ""):
+                    best = {"bytes": float(row["dram_read_bytes"]) + float(row["dram_write_bytes"]),
+                            "src": os.path.relpath(path, ROOT), "batch": int(row.get("batch", 0) or 0)}
+        except Exception:
+            continue
+    return best
 
 
 # ----------------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port on the host cores
+# the reference itself (unmodified modules.py / mtad_gat.py staged under baseline/_ref)
 # ----------------------------------------------------------------------------------------------------------
-def cpu_port_rate(sample_b, reps, seed=0):
-    """windows/s of the numpy port of the reference path (forward as written + backward), fp32, `sample_b`
-    windows per pass.  Adam is excluded (it is <1% of the CPU time)."""
+def load_reference():
+    """Import MTAD_GAT from baseline/_ref (never from the package under test).  None when it was not staged."""
+    if not os.path.exists(os.path.join(REF_DIR, "mtad_gat.py")):
+        return None
+    for name in ("modules", "mtad_gat"):
+        sys.modules.pop(name, None)
+    sys.path.insert(0, REF_DIR)
+    try:
+        mod = importlib.import_module("mtad_gat")
+    finally:
+        sys.path.remove(REF_DIR)
+    assert os.path.samefile(os.path.dirname(mod.__file__), REF_DIR)
+    return mod.MTAD_GAT
+
+
+def reference_rate(cfgname, batch, steps, warmup, device, gatv1=False, budget_s=150.0):
+    """windows/s of the reference's own step (training.py:109-127: zero_grad, forward, sqrt-MSE losses, backward,
+    Adam.step) or no_grad forward (prediction.py:50-55), fp32, on `device`.  Returns (mean_rate, best_rate, times_s)."""
+    import torch
+    RefModel = load_reference()
+    if RefModel is None:
+        return None
+    c = CONFIGS[cfgname]
+    kw = dict(c["kw"])
+    if gatv1:
+        kw["use_gatv2"] = False
+    torch.manual_seed(0)
+    model = RefModel(**kw).to(device)
+    k, n = kw["n_features"], kw["window_size"]
+    x = torch.rand(batch, n, k).to(device)
+    y = torch.rand(batch, 1, k).to(device)
+    td = [0] if kw["out_dim"] == 1 else None
+    crit = torch.nn.MSELoss()
+    times = []
+    if c["train"]:
+        model.train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+        def one():
+            opt.zero_grad()
+            preds, recons = model(x)
+            xx, yy = x, y
+            if td is not None:
+                xx = x[:, :, td]; yy = y[:, :, td].squeeze(-1)
+            if preds.ndim == 3:
+                preds = preds.squeeze(1)
+            if yy.ndim == 3:
+                yy = yy.squeeze(1)
+            loss = torch.sqrt(crit(yy, preds)) + torch.sqrt(crit(xx, recons))
+            loss.backward()
+            opt.step()
+            return loss
+    else:
+        model.eval()
+
+        def one():
+            with torch.no_grad():
+                return model(x)[0]
+    cuda = str(device).startswith("cuda")
+    t_begin = time.perf_counter()
+    for i in range(warmup + steps):
+        if len(times) >= 2 and time.perf_counter() - t_begin > budget_s:
+            break                                    # bounded sample: the run must end within a few minutes
+        if cuda:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = one()
+        if cuda:
+            torch.cuda.synchronize()
+        else:
+            float(r.detach().sum())
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    mean = batch / (sum(times) / len(times))
+    return mean, batch / min(times), times
+
+
+def cpu_model_name():
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                return l.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def oracle_port_rate(cfgname, sample_b, reps):
+    """Fallback when baseline/_ref is absent: the numpy port of the reference path (oracle/), forward + backward."""
     from oracle import mtad_gat_oracle as orc
-    cfg = orc.Config(**MODEL_KW)
-    params = orc.make_params(cfg, seed=seed, dtype=np.float32)
-    rng = np.random.default_rng(seed)
-    x = rng.random((sample_b, N_WIN, K_FEAT)).astype(np.float32)
-    y = rng.random((sample_b, 1, K_FEAT)).astype(np.float32)
-    orc.loss_fwd_bwd(x, y, params, cfg)            # warm-up (BLAS threads, page faults)
+    kw = CONFIGS[cfgname]["kw"]
+    cfg = orc.Config(**kw)
+    params = orc.make_params(cfg, seed=0, dtype=np.float32)
+    rng = np.random.default_rng(0)
+    x = rng.random((sample_b, cfg.n, cfg.k)).astype(np.float32)
+    y = rng.random((sample_b, 1, cfg.k)).astype(np.float32)
+    orc.loss_fwd_bwd(x, y, params, cfg)
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
         orc.loss_fwd_bwd(x, y, params, cfg)
         times.append(time.perf_counter() - t0)
-    return sample_b / min(times), sample_b / (sum(times) / len(times)), times
+    return sample_b / (sum(times) / len(times)), sample_b / min(times), times
 
 
 def run_reference(args):
+    """The reference arm: the UNMODIFIED reference (baseline/_ref) on this box's host cores, same config; each step is
+    one full reference step at the reference batch (C2: the same 256-window batch as our arm)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_b = 16
+    import torch
     cores = os.cpu_count()
-    # warmup passes
-    for _ in range(max(0, args.warmup - 1)):
-        cpu_port_rate(sample_b, 1)
-    best, mean, times = cpu_port_rate(sample_b, max(1, args.steps))
+    torch.set_num_threads(cores)
+    c = CONFIGS[args.config]
+    rb = c["ref_batch"]
+    res = reference_rate(args.config, rb, max(1, args.steps), max(1, min(args.warmup, 2)), "cpu", args.gatv1)
+    kind = "reference"
+    if res is None:
+        kind = "port"
+        rb = 16
+        res = oracle_port_rate(args.config, rb, max(1, min(args.steps, 5)))
+    mean, best, times = res
     ms = 1e3 * sum(times) / len(times)
+    sample = (f"{len(times)} timed steps of the unmodified reference (baseline/_ref mtad_gat.py + modules.py, torch "
+              f"{torch.__version__} CPU, {cores} threads, fp32) at batch {rb}" if kind == "reference" else
+              f"{len(times)} timed {rb}-window fwd+bwd passes of the numpy port (oracle/): baseline/_ref was not staged")
     line = {
-        "impl": "reference", "metric": "windows/sec MTAD-GAT fwd+bwd (k=38,n=100)", "value": mean, "unit": "windows/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": f"{sample_b} windows per step on the CPU"},
-        "cpu_baseline": {"value": mean, "unit": "windows/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_b}-window fwd+bwd passes of the numpy port (oracle/), {len(times)} timed"},
+        "impl": "reference", "metric": metric_name(args.config), "value": mean, "unit": "windows/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": c["label"], "reference_batch": rb, "same_config": rb == c["batch"] and kind == "reference",
+                   "gat": "v1" if args.gatv1 else "v2", "cpu": cpu_model_name()},
+        "cpu_baseline": {"value": mean, "unit": "windows/s", "cores": cores, "kind": kind, "sample": sample,
+                         "best": best},
         "e2e": {"value": mean, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -99,7 +237,7 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.samples = []          # (sm_mhz, [reason flags])
+        self.samples = []          # (sm_mhz, [reason flags], power_w)
         self.sm_max = None
         self.source = None
         self.stop = threading.Event()
@@ -124,7 +262,11 @@ class ClockSampler:
         r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
         flags = [bool(r & nv.nvmlClocksEventReasonHwSlowdown), bool(r & nv.nvmlClocksEventReasonHwThermalSlowdown),
                  bool(r & nv.nvmlClocksEventReasonSwThermalSlowdown), bool(r & nv.nvmlClocksEventReasonSwPowerCap)]
-        self.samples.append((sm, flags))
+        try:
+            pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+        except Exception:
+            pw = None
+        self.samples.append((sm, flags, pw))
 
     def _sample_smi(self):
         out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.FIELDS}",
@@ -132,7 +274,11 @@ class ClockSampler:
         parts = [p.strip() for p in out.strip().split(",")]
         if len(parts) >= 7 and parts[0].replace(".", "").isdigit():
             self.sm_max = float(parts[1])
-            self.samples.append((float(parts[0]), [parts[3 + i].lower().startswith("active") for i in range(4)]))
+            try:
+                pw = float(parts[2])
+            except ValueError:
+                pw = None
+            self.samples.append((float(parts[0]), [parts[3 + i].lower().startswith("active") for i in range(4)], pw))
 
     def _run(self):
         while not self.stop.is_set():
@@ -159,8 +305,98 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["clock sampling unavailable"], "samples": 0}
         sm = sorted(s[0] for s in self.samples)
         reasons = [n for i, n in enumerate(self.NAMES) if any(s[1][i] for s in self.samples)]
+        pws = [s[2] for s in self.samples if s[2] is not None]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(self.samples),
-                "source": self.source}
+                "power_w_max": max(pws) if pws else None, "source": self.source}
+
+
+class ForwardStep:
+    """Forward-only scoring step (C3): one no_grad forward of a static batch, optionally replayed from a CUDA graph,
+    with the same host-input pipeline interface as training.TrainStep."""
+
+    def __init__(self, model, batch, use_graph=True):
+        import torch
+        p0 = next(model.parameters())
+        n, k = model.temporal_gat.window_size, model.temporal_gat.n_features
+        self.model, self.use_graph = model, use_graph
+        self.x = torch.zeros(batch, n, k, device=p0.device)
+        self.preds = self.recons = None
+        self.g = None
+        self.launches_per_step = 0
+        self._stage = [torch.zeros_like(self.x) for _ in range(2)]
+        self._copy_stream = torch.cuda.Stream(device=p0.device)
+        self._ev = [None, None]
+        self._put = self._get = 0
+        self._host = None
+
+    def _fwd(self):
+        import torch
+        with torch.no_grad():
+            self.preds, self.recons = self.model(self.x)
+
+    def _run(self):
+        import torch
+        import mtad_gat_pytorch_b200 as mg
+        if not self.use_graph:
+            self._fwd()
+            return
+        if self.g is None:
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(2):
+                    self._fwd()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            mg.reset_launch_count()
+            self.g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g, stream=s):
+                self._fwd()
+            self.launches_per_step = mg.launch_count()
+        self.g.replay()
+
+    def run_device(self, x, y=None):
+        self.x.copy_(x)
+        self._run()
+
+    def prefetch_host(self, x_host, y_host=None):
+        import torch
+        slot = self._put & 1
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cs):
+            self._stage[slot].copy_(x_host, non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(cs)
+        self._ev[slot] = ev
+        self._put += 1
+
+    def launch_prefetched(self):
+        import torch
+        slot = self._get & 1
+        self._get += 1
+        torch.cuda.current_stream().wait_event(self._ev[slot])
+        self.x.copy_(self._stage[slot])
+        self._run()
+        if self._host is None:
+            self._host = [(torch.zeros_like(self.preds, device="cpu").pin_memory(),
+                           torch.zeros_like(self.recons, device="cpu").pin_memory()) for _ in range(2)]
+            self._hev = [None, None]
+            self._hput = self._hget = 0
+        k = self._hput & 1
+        self._hput += 1
+        self._host[k][0].copy_(self.preds, non_blocking=True)
+        self._host[k][1].copy_(self.recons, non_blocking=True)
+        ev = torch.cuda.Event(); ev.record()
+        self._hev[k] = ev
+
+    def collect(self):
+        k = self._hget & 1
+        self._hget += 1
+        self._hev[k].synchronize()
+        return float(self._host[k][0].sum())
+
+    def d2h_bytes(self):
+        return int(self.preds.numel() * 4 + self.recons.numel() * 4)
 
 
 def run_ours(args):
@@ -176,19 +412,34 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    c = CONFIGS[args.config]
+    kw = dict(c["kw"])
+    if args.gatv1:
+        kw["use_gatv2"] = False
+    k, n = kw["n_features"], kw["window_size"]
+    base_b = args.batch or c["batch"]
+    if args.scaling == "strong":
+        lo, hi = mgt.shard_batch(base_b, world, rank)
+        B, global_b = hi - lo, base_b
+    else:
+        B, global_b = base_b, base_b * world
     if args.gru_split:
         mg.set_gru_split(args.gru_split)
     torch.manual_seed(0)
-    model = mg.MTAD_GAT(**MODEL_KW).to(dev)
-    model.train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=not args.no_graph, fused=True)
-    step = mgt.TrainStep(model, opt, batch=B, use_graph=not args.no_graph, world_size=world)
+    model = mg.MTAD_GAT(**kw).to(dev)
+    model.train(c["train"])
+    if c["train"]:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=not args.no_graph, fused=True)
+        step = mgt.TrainStep(model, opt, batch=B, use_graph=not args.no_graph, world_size=world,
+                             target_dims=[0] if kw["out_dim"] == 1 else None, capture_comm=not args.eager_comm,
+                             overlap_comm=not args.no_overlap_comm, pipeline=args.pipeline)
+    else:
+        step = ForwardStep(model, B, use_graph=not args.no_graph)
 
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    n_host = 8
-    xs_host = [torch.rand(B, N_WIN, K_FEAT, generator=g).pin_memory() for _ in range(n_host)]
-    ys_host = [torch.rand(B, 1, K_FEAT, generator=g).pin_memory() for _ in range(n_host)]
+    n_host = 4 if B * n * k * 4 > (64 << 20) else 8
+    xs_host = [torch.rand(B, n, k, generator=g).pin_memory() for _ in range(n_host)]
+    ys_host = [torch.rand(B, 1, k, generator=g).pin_memory() for _ in range(n_host)]
     xs_dev = [t.to(dev) for t in xs_host]
     ys_dev = [t.to(dev) for t in ys_host]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
@@ -199,7 +450,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- warm-up (also captures the CUDA graph) ----
-    for i in range(max(args.warmup, 3)):
+    W = max(args.warmup, 3)
+    for i in range(W):
         step.run_device(xs_dev[i % n_host], ys_dev[i % n_host])
     barrier()
 
@@ -219,12 +471,12 @@ def run_ours(args):
         ms_dev = sum(a.elapsed_time(b) for a, b in evs) / args.steps
         launches = step.launches_per_step * args.steps if step.launches_per_step else mg.launch_count()
 
-        # ---- e2e: host pinned inputs -> H2D -> step -> D2H loss, wall clock over K steps ----
+        # ---- e2e: host pinned inputs -> H2D -> step -> D2H result, wall clock over K steps ----
         barrier()
         t0 = time.perf_counter()
         last = None
-        # software pipeline of the training loop: H2D of batch i+1 (copy stream) and the host-side enqueue of step
-        # i+1 overlap step i; every step still copies its batch in and its loss out (the loss of step i is read on
+        # software pipeline of the caller's loop: H2D of batch i+1 (copy stream) and the host-side enqueue of step
+        # i+1 overlap step i; every step still copies its batch in and its result out (the result of step i is read on
         # the host after step i+1 has been enqueued)
         step.prefetch_host(xs_host[0], ys_host[0])
         for i in range(args.steps):
@@ -237,6 +489,21 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / args.steps     # local wall time; MAX over ranks below (the closing
         barrier()                                           # collective barrier itself is not part of the K steps)
+
+        # ---- sustained: the same device-resident loop for ~2 s without the per-step flush bookkeeping (burst vs
+        #      sustained clocks; reported next to `value`, never instead of it) ----
+        sustained = None
+        if args.sustain_s > 0:
+            n_s = max(args.steps, int(args.sustain_s / (ms_dev * 1e-3)))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            e0.record()
+            for i in range(n_s):
+                flush.zero_()
+                step.run_device(xs_dev[i % n_host], ys_dev[i % n_host])
+            e1.record()
+            barrier()
+            sustained = {"steps": n_s, "ms_per_step_incl_flush": e0.elapsed_time(e1) / n_s}
     t_ms = torch.tensor([ms_dev, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -245,34 +512,66 @@ def run_ours(args):
     if rank == 0:
         peaks = load_peaks()
         from mtad_gat_pytorch_b200 import kernel_bench
-        kern = kernel_bench.stage_rooflines(model, B, peaks, dev)
-        # dominant single kernel = the slower of the two persistent recurrence launches (largest share of the step,
-        # profiles/r1_launches_bench.csv); the other rows are whole stages (several launches each)
+        pipes = getattr(step, "pipeline", 1)
+        rec_b = B if pipes == 1 else (B // pipes + 15) // 16 * 16
+        kern = kernel_bench.stage_rooflines(model, B, peaks, dev, train=c["train"], rec_batch=rec_b)
+        # dominant single kernel = the slowest single launch of the step among the persistent recurrences and the GAT
+        # score kernels (profiles/*launches*.csv has the full list); the other rows are whole stages (several launches)
         single = [r for r in kern if r.get("single_kernel")]
         dominant = max(single or kern, key=lambda r: r["ms"])
-        if B == BATCH and dominant["kernel"] in NCU_TRAFFIC:
-            dominant["traffic"] = NCU_TRAFFIC[dominant["kernel"]]
-        roof = {k_: dominant[k_] for k_ in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
-        roof["kernel"] = dominant["kernel"]
-        roof["peak_src"] = peaks["src"]
+        tr = ncu_traffic(dominant.get("ncu_name", dominant["kernel"]))
+        roof = {k_: dominant[k_] for k_ in ("bound", "achieved", "peak", "unit", "frac")}
+        roof.update({"traffic": tr["bytes"] if tr and tr["batch"] in (0, rec_b) else None,
+                     "traffic_src": tr["src"] if tr and tr["batch"] in (0, rec_b) else None, "windows_per_launch": rec_b,
+                     "kernel": dominant["kernel"], "ms": dominant["ms"], "alg_bytes": dominant["alg_bytes"],
+                     "alg_bytes_def": dominant.get("alg_bytes_def"), "operand_bytes": dominant.get("operand_bytes"),
+                     "frac_operand_bytes": dominant.get("frac_operand_bytes"), "frac_tensor": dominant.get("frac_tensor"),
+                     "peak_src": peaks["src"]})
         cpu = None
+        ref_cuda = None
         if world == 1 and not args.skip_cpu:
-            best, mean, times = cpu_port_rate(16, 3)
-            cpu = {"value": mean, "unit": "windows/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"3 timed 16-window fwd+bwd passes of the numpy port of the reference path ({sum(times):.1f} s)"}
+            torch.set_num_threads(os.cpu_count())
+            res = reference_rate(args.config, c["ref_batch"], 3 if c["ref_batch"] >= 64 else 2, 1, "cpu", args.gatv1)
+            if res is not None:
+                mean, best, times = res
+                cpu = {"value": mean, "best": best, "unit": "windows/s", "cores": os.cpu_count(), "kind": "reference",
+                       "cpu": cpu_model_name(),
+                       "sample": f"{len(times)} timed steps (after 1 warm-up) of the unmodified reference (baseline/_ref, torch CPU "
+                                 f"fp32, {os.cpu_count()} threads) at batch {c['ref_batch']} ({sum(times):.1f} s)"}
+            else:
+                mean, best, times = oracle_port_rate(args.config, 16, 3)
+                cpu = {"value": mean, "unit": "windows/s", "cores": os.cpu_count(), "kind": "port",
+                       "sample": f"3 timed 16-window fwd+bwd passes of the numpy port (oracle/); baseline/_ref not staged ({sum(times):.1f} s)"}
+        if world == 1 and not args.skip_ref_cuda:
+            try:
+                rb = c["ref_batch"]
+                res = reference_rate(args.config, rb, 10, 3, dev, args.gatv1)
+                if res is not None:
+                    ref_cuda = {"value": res[0], "best": res[1], "unit": "windows/s", "batch": rb,
+                                "what": "the unmodified reference model on this GPU, eager PyTorch (cuBLAS/cuDNN sm_100 kernels), "
+                                        "wall clock with synchronize per step; informative"}
+            except Exception as e:                                   # e.g. out of memory at the larger shapes
+                ref_cuda = {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
+            torch.cuda.empty_cache()
+        h2d = int(xs_host[0].numel() * 4 + (ys_host[0].numel() * 4 if c["train"] else 0))
+        d2h = 8 if c["train"] else step.d2h_bytes()
         line = {
-            "metric": "windows/sec MTAD-GAT fwd+bwd (k=38,n=100)", "value": B * world / (ms_dev * 1e-3), "unit": "windows/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": B * world, "parallelism": f"dp{world}",
-                       "e2e_loop": "pinned host batches, H2D of batch i+1 and enqueue of step i+1 overlap step i, loss of every step copied back",
+            "metric": metric_name(args.config), "value": global_b / (ms_dev * 1e-3), "unit": "windows/s",
+            "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_dev,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": c["label"], "global_batch": global_b, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                       "gat": "v1" if args.gatv1 else "v2",
+                       "arithmetic": "fp32 storage/accumulate; GEMMs bf16x3 on tcgen05, recurrences fp16 operands on tcgen05",
+                       "e2e_loop": "pinned host batches, H2D of batch i+1 and enqueue of step i+1 overlap step i, result of every step copied back",
                        "cuda_graph": not args.no_graph, "l2": "256 MiB buffer zeroed between timed steps",
-                       "optimizer": "torch.optim.Adam(fused) inside the step"},
-            "e2e": {"value": B * world / (e2e_ms * 1e-3), "unit": "windows/s",
-                    "h2d_bytes_per_step": int(xs_host[0].numel() * 4 + ys_host[0].numel() * 4), "d2h_bytes_per_step": 8,
-                    "ms_per_step": e2e_ms},
+                       "optimizer": "torch.optim.Adam(fused) inside the step" if c["train"] else None,
+                       "comm": None if world == 1 else ("captured in the step graph" if not args.eager_comm else "eager between graphs"),
+                       "pipeline": getattr(step, "pipeline", 1)},
+            "e2e": {"value": global_b / (e2e_ms * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
             "gpu_launches": int(launches), "roofline": roof, "kernels": kern, "cpu_baseline": cpu,
-            "clocks": clocks.summary(), "wall_s_timed": t_wall, "loss": last,
+            "reference_cuda": ref_cuda, "sustained": sustained,
+            "clocks": clocks.summary(), "wall_s_timed": t_wall, "result": last,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -282,15 +581,27 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"])
+    ap.add_argument("--gatv1", action="store_true", help="use_gatv2=False (the HBM-bound GAT variant)")
+    ap.add_argument("--batch", type=int, default=0, help="override the config's batch")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--eager-comm", action="store_true", help="keep the gradient all-reduce out of the step graph")
+    ap.add_argument("--no-overlap-comm", action="store_true", help="one all-reduce at the end of backward")
+    ap.add_argument("--pipeline", type=int, default=-1, help="micro-batch pipelines inside the step (-1 = auto)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-ref-cuda", action="store_true")
+    ap.add_argument("--sustain-s", type=float, default=2.0)
     ap.add_argument("--gru-split", type=int, default=0, help="clusters per 16-window tile in the recurrence (0 = auto)")
     args = ap.parse_args()
+    if args.scaling is None:
+        args.scaling = "strong" if CONFIGS[args.config]["batch_is_global"] else "weak"
     if args.impl == "reference":
+        if args.steps == 200:
+            args.steps = 5
         run_reference(args)
     else:
         run_ours(args)

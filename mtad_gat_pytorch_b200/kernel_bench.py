@@ -20,7 +20,7 @@ def _time(fn, flush, reps=7):
     return ts[len(ts) // 2]
 
 
-def stage_rooflines(model, B, peaks, dev):
+def stage_rooflines(model, B, peaks, dev, train=True, rec_batch=None):
     n, k = model.temporal_gat.window_size, model.temporal_gat.n_features
     H = model.gru.hid_dim
     R = model.recon_model.decoder.rnn.hidden_size
@@ -45,12 +45,15 @@ def stage_rooflines(model, B, peaks, dev):
         o = outs["o"]
         o_list = [t for t in (o if isinstance(o, (tuple, list)) else [o]) if t.requires_grad]
         go = [torch.ones_like(t) for t in o_list]
-        ms_b = _time(lambda: torch.autograd.grad(o_list, inputs, go, retain_graph=True, allow_unused=True), flush)
-        for tag, ms, by, fl in (("fwd", ms_f, bytes_f, flops_f), ("bwd", ms_b, 1.5 * bytes_f, 2.0 * flops_f)):
+        stages = [("fwd", ms_f, bytes_f, flops_f)]
+        if train:
+            ms_b = _time(lambda: torch.autograd.grad(o_list, inputs, go, retain_graph=True, allow_unused=True), flush)
+            stages.append(("bwd", ms_b, 1.5 * bytes_f, 2.0 * flops_f))
+        for tag, ms, by, fl in stages:
             if bound == "hbm":
                 ach, peak, unit = by / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
             else:
-                ach, peak, unit = fl / (ms * 1e-3) / 1e12, peaks["bf16_tflops"], "TFLOP/s"
+                ach, peak, unit = fl / (ms * 1e-3) / 1e12, peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]), "TFLOP/s"
             rows.append({"kernel": f"{name}_{tag}", "ms": ms, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
                          "frac": ach / peak, "traffic": None, "alg_bytes": by, "dense_flops": fl})
 
@@ -75,16 +78,24 @@ def stage_rooflines(model, B, peaks, dev):
     rp = list(model.recon_model.parameters())
     add("recon", lambda: model.recon_model(h_end), [h_end] + rp, (H + n * out_dim) * 4 * B,
         (2 * n * R * 3 * R + 2 * n * R * out_dim) * B, "tensor")
-    rows += recurrence_rooflines(B, n, H, model.gru.gru.weight_hh_l0.detach(), model.gru.gru.bias_hh_l0.detach(), peaks, dev, flush)
+    # the recurrence launches as the step issues them: with micro-batch pipelines each launch covers one slice
+    rows += recurrence_rooflines(rec_batch or B, n, k, H, model.gru.gru.weight_hh_l0.detach(), model.gru.gru.bias_hh_l0.detach(), peaks, dev,
+                                 flush, train)
     model.train(was_training)
     del flush
     return rows
 
 
-def recurrence_rooflines(B, n, H, w_hh, b_hh, peaks, dev, flush):
+def recurrence_rooflines(B, n, k, H, w_hh, b_hh, peaks, dev, flush, train=True):
     """The recurrence launches alone (mtadgat_gru_recurrence_fwd / _bwd = the persistent cluster kernels; the BPTT entry
-    also runs a 5 us absmax pre-pass) on synthetic window-tiled operands.  Algorithmic bytes: every operand read or
-    written once (fp32); FLOPs: the h_{t-1} W_hh^T products (2*3H*H per window and step, same for dh)."""
+    also runs a 5 us absmax pre-pass) on synthetic window-tiled operands -- the largest single kernels of the step.
+
+    alg_bytes follows SURVEY.md section 8(d) for the encoder GRU: (3nk + H + nH) * 4 bytes per window forward (x-slices in,
+    h_end out, the n saved states of training), 1.5x that backward; `frac` = alg_bytes / time / measured HBM copy
+    bandwidth.  operand_bytes is what this kernel's own interface moves (window-tiled gi in, gates out, ...): larger,
+    because the input projection and the gate cache live in HBM; frac_operand_bytes is reported next to it.
+    frac_tensor: the h W_hh^T products (2*3H*H flop per window and step) against the BURST bf16 peak (a kernel timed
+    alone).  The kernel is bound by neither: it is a chain of n dependent steps."""
     from ._lib import lib
     Bp = (B + 15) // 16 * 16
     st = torch.cuda.current_stream().cuda_stream
@@ -99,21 +110,28 @@ def recurrence_rooflines(B, n, H, w_hh, b_hh, peaks, dev, flush):
     gmax = torch.zeros(1, dtype=torch.int32, device=dev)
     w_hh = w_hh.contiguous(); b_hh = b_hh.contiguous()
     f = lambda: F.check(lib.mtadgat_gru_recurrence_fwd(gi.data_ptr(), w_hh.data_ptr(), b_hh.data_ptr(), wt.data_ptr(),
-                                                      out.data_ptr(), hl.data_ptr(), gates.data_ptr(), B, n, H, st))
+                                                      out.data_ptr(), hl.data_ptr(), gates.data_ptr() if train else None,
+                                                      B, n, H, st))
     b = lambda: F.check(lib.mtadgat_gru_recurrence_bwd(gates.data_ptr(), out.data_ptr(), w_hh.data_ptr(), dout.data_ptr(),
                                                       None, dgi.data_ptr(), dghn.data_ptr(), gmax.data_ptr(), B, n, H, st))
-    ms_f = _time(f, flush, reps=9)
-    ms_b = _time(b, flush, reps=9)
+    f()
+    todo = [("gru_recurrence_fwd_kernel", "gru_cl_fwd_kernel", _time(f, flush, reps=9), 1.0,
+             4.0 * n * (Bp * 3 * H + B * H + (Bp * 4 * H if train else 0)))]
+    if train:
+        todo.append(("gru_recurrence_bwd_kernel", "gru_cl_bwd_kernel", _time(b, flush, reps=9), 1.5,
+                     4.0 * n * (Bp * 4 * H + 2 * B * H + Bp * 4 * H + B * H)))
     flops = 2.0 * 3 * H * H * n * B
-    by_f = 4.0 * n * (Bp * 3 * H + B * H + Bp * 4 * H)
-    by_b = 4.0 * n * (Bp * 4 * H + 2 * B * H + Bp * 4 * H + B * H)
+    alg_f = (3 * n * k + H + n * H) * 4.0 * B
+    burst = peaks.get("bf16_tflops", peaks.get("bf16_tflops_sustained"))
     rows = []
-    for name, ms, by in (("gru_recurrence_fwd_kernel", ms_f, by_f), ("gru_recurrence_bwd_kernel", ms_b, by_b)):
-        hb, tf = by / (ms * 1e-3) / 1e9, flops / (ms * 1e-3) / 1e12
-        fh, ft = hb / peaks["hbm_gbs"], tf / peaks["bf16_tflops"]
-        bound = "hbm" if fh >= ft else "tensor"
-        rows.append({"kernel": name, "ms": ms, "bound": bound, "achieved": hb if bound == "hbm" else tf,
-                     "peak": peaks["hbm_gbs"] if bound == "hbm" else peaks["bf16_tflops"],
-                     "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": max(fh, ft), "traffic": None,
-                     "alg_bytes": by, "dense_flops": flops, "frac_hbm": fh, "frac_tensor": ft, "single_kernel": True})
+    for name, ncu_name, ms, mult, operand in todo:
+        alg = mult * alg_f
+        hb = alg / (ms * 1e-3) / 1e9
+        tf = flops / (ms * 1e-3) / 1e12
+        rows.append({"kernel": name, "ncu_name": ncu_name, "ms": ms, "bound": "hbm", "achieved": hb, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "frac": hb / peaks["hbm_gbs"], "traffic": None, "alg_bytes": alg,
+                     "alg_bytes_def": f"SURVEY 8(d) encoder GRU: (3nk+H+nH)*4*B{' * 1.5 (bwd)' if mult > 1 else ''}",
+                     "operand_bytes": operand, "frac_operand_bytes": operand / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "dense_flops": flops, "frac_tensor": tf / burst, "frac_hbm": hb / peaks["hbm_gbs"],
+                     "single_kernel": True})
     return rows

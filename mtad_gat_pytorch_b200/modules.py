@@ -83,12 +83,14 @@ class TemporalAttentionLayer(_GraphAttention):
     _feature = False
 
 
-def _gru_stack(rnn, layer0, n_layers, p_between, training, seed_fn):
-    """Layers 1.. of an nn.GRU parameter container on top of `layer0`'s per-step outputs."""
+def _gru_stack(rnn, layer0, n_layers, p_between, training, seed_fn, rng_base):
+    """Layers 1.. of an nn.GRU parameter container on top of `layer0`'s per-step outputs.  `rng_base` is the Philox
+    stream id of the inter-layer dropout: the encoder and the decoder receive the same per-step seed, so they need
+    distinct stream ids to draw independent masks (as the reference's two nn.GRU modules do)."""
     out, h_last = layer0
     for l in range(1, n_layers):
         if training and p_between > 0.0:     # nn.GRU inter-layer dropout (modules.py:231-233)
-            m = F.dropout_multipliers(out.numel(), p_between, seed_fn(), F.RNG_GRU0 + l).view_as(out)
+            m = F.dropout_multipliers(out.numel(), p_between, seed_fn(), rng_base + l).view_as(out)
             out = out * m
         out, h_last = F.GruFn.apply(out, None, None, getattr(rnn, f"weight_ih_l{l}"), getattr(rnn, f"weight_hh_l{l}"),
                                     getattr(rnn, f"bias_ih_l{l}"), getattr(rnn, f"bias_hh_l{l}"), True)
@@ -114,7 +116,7 @@ class GRULayer(nn.Module, _SeedMixin):
         if multi:
             dev = xs[0].device
             return _gru_stack(g, layer0, self.n_layers, self.dropout, self.training,
-                              lambda: self._step_seed if self._step_seed is not None else F.fresh_seed(dev))
+                              lambda: self._step_seed if self._step_seed is not None else F.fresh_seed(dev), F.RNG_GRU0)
         return layer0
 
     def forward_slices(self, slices):
@@ -141,7 +143,7 @@ class RNNDecoder(nn.Module, _SeedMixin):
         if self.n_layers == 1:
             return out
         return _gru_stack(self.rnn, (out, None), self.n_layers, self.dropout, self.training,
-                          lambda: self._step_seed if self._step_seed is not None else F.fresh_seed(dev))[0]
+                          lambda: self._step_seed if self._step_seed is not None else F.fresh_seed(dev), F.RNG_DEC0)[0]
 
     def forward_repeat(self, h_end, window_size):
         """Decoder over the reference's scrambled repeat of h_end (modules.py:279) without building it."""

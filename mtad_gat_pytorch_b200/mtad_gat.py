@@ -32,9 +32,12 @@ class MTAD_GAT(nn.Module):
         self._side = {}
 
     def _side_stream(self, device):
-        s = self._side.get(device)
+        """The branch stream paired with the CURRENT stream (one per main stream: micro-batch pipelines that run this
+        forward on different streams must not serialise on a shared side stream)."""
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        s = self._side.get(key)
         if s is None:
-            s = self._side[device] = torch.cuda.Stream(device=device)
+            s = self._side[key] = torch.cuda.Stream(device=device)
         return s
 
     def _seeded(self):

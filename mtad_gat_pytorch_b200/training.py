@@ -27,7 +27,8 @@ def rmse_losses(x, y, preds, recons, target_dims=None):
 
 def allreduce_gradients(params, world_size):
     """Average the gradients of `params` across ranks with ONE flat-bucket all-reduce (1.6 MB at SMD shape).
-    Backend-agnostic (NCCL on the GPUs, gloo in the CPU tests)."""
+    Backend-agnostic (NCCL on the GPUs, gloo in the CPU tests).  Generic path: flatten, reduce, copy back; TrainStep
+    avoids both copies by having the backward kernels write straight into a GradBucket."""
     if world_size == 1:
         return
     grads = [p.grad for p in params]
@@ -40,6 +41,41 @@ def allreduce_gradients(params, world_size):
     torch._foreach_copy_(grads, torch._utils._unflatten_dense_tensors(flat, grads))
 
 
+class GradBucket:
+    """One flat fp32 buffer that the weight-gradient kernels write into directly (functional._grad_out hands every
+    backward a view of it instead of a fresh tensor, and autograd adopts that view as `.grad`): the all-reduce runs on
+    the buffer in place -- no flatten before, no copy back after.
+
+    Parameters are laid out in two contiguous groups, in the order backpropagation finishes them:
+      early = heads + decoder + encoder GRU (1.03 MB at SMD shape; complete when the encoder BPTT has been issued),
+      late  = conv + the two GAT layers (complete at the end of backward).
+    The early group is reduced on a communication stream while the GAT/conv backward still runs."""
+
+    def __init__(self, model):
+        early, late = [], []
+        for name, p in model.named_parameters():
+            if not p.requires_grad:
+                continue
+            (late if name.startswith(("conv.", "feature_gat.", "temporal_gat.")) else early).append(p)
+        self.params = early + late
+        ALIGN = 64                         # floats: every slot starts on a 256-byte boundary (vectorised stores in the
+        offs, off = [], 0                  # weight-gradient kernels); the zero padding rides along in the all-reduce
+        for p in self.params:
+            offs.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        total = off
+        n_early = offs[len(early)] if late else total
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.params[0].device)
+        self.early = self.flat.narrow(0, 0, n_early)
+        self.late = self.flat.narrow(0, n_early, total - n_early)
+        self.sinks = {id(p): (self.flat, o) for p, o in zip(self.params, offs)}
+
+    def adopted(self):
+        """True when every parameter's .grad aliases its slot of the bucket (autograd adopted the views)."""
+        return all(p.grad is not None and p.grad.data_ptr() == self.flat.data_ptr() + 4 * off
+                   for p in self.params for (_, off) in [self.sinks[id(p)]])
+
+
 def shard_batch(global_batch, world_size, rank):
     """Windows shard over the batch: contiguous [lo, hi) slice of the global batch owned by `rank`."""
     base, rem = divmod(global_batch, world_size)
@@ -48,7 +84,16 @@ def shard_batch(global_batch, world_size, rank):
 
 
 class TrainStep:
-    def __init__(self, model, optimizer, batch, use_graph=True, world_size=1, target_dims=None):
+    """training.py:106-127 of the reference as one replayable unit.
+
+    world_size > 1 (one process per GPU, NCCL): gradients land in a GradBucket; its early half is all-reduced on a
+    communication stream as soon as the encoder BPTT has been issued (overlapping the GAT / conv backward), the late
+    half at the end of backward; with `use_graph` the collectives are captured INTO the step graph together with
+    fused Adam, so a step is a single graph replay at any world size (`capture_comm=False` keeps the collective
+    eager between two graphs)."""
+
+    def __init__(self, model, optimizer, batch, use_graph=True, world_size=1, target_dims=None, capture_comm=True,
+                 overlap_comm=True, pipeline=-1):
         p0 = next(model.parameters())
         self.model, self.opt, self.world = model, optimizer, world_size
         self.target_dims = target_dims
@@ -58,6 +103,28 @@ class TrainStep:
         self.losses = torch.zeros(2, device=p0.device)
         self.params = [p for p in model.parameters() if p.requires_grad]
         self.use_graph = use_graph
+        # micro-batch pipelines: the step's critical path is four strictly serial 100-step recurrences (latency-, not
+        # throughput-bound: 64 SMs run them as fast as 128), so the batch is split into `pipeline` contiguous slices that
+        # run forward and backward on their own streams -- one slice's recurrences overlap the other's GAT / GEMM work.
+        # The loss is still the reference's sqrt(MSE) over the WHOLE batch (the slices join at the loss), and the
+        # slices' parameter gradients are summed, so the step computes exactly what the unsplit step does.
+        if pipeline < 0:
+            pipeline = 2 if (p0.is_cuda and batch >= 128 and batch % 32 == 0) else 1
+        self.pipeline = max(1, pipeline)
+        self._pipe_streams = [torch.cuda.Stream(device=p0.device) for _ in range(self.pipeline)] if self.pipeline > 1 else []
+        # slice i > 0 runs the model on ALIASES of the parameters (same storage, separate autograd leaves): each slice
+        # then owns its gradient tensors and no accumulation kernel races with the parameter-gradient side streams
+        self._names = [nm for nm, p in model.named_parameters() if p.requires_grad]
+        self._alias = [{nm: p.detach().requires_grad_() for nm, p in model.named_parameters() if p.requires_grad}
+                       for _ in range(self.pipeline - 1)]
+        self.bucket = None
+        self.capture_comm = capture_comm
+        self.overlap_comm = overlap_comm
+        self._comm_stream = None
+        self._early_work = None
+        if world_size > 1 and p0.is_cuda and dist.get_backend() == "nccl":
+            self.bucket = GradBucket(model)
+            self._comm_stream = torch.cuda.Stream(device=p0.device)
         # host-input pipeline: two device staging buffers filled by a copy stream, so the H2D copy of batch i+1
         # overlaps the step on batch i (every batch is still copied inside the timed region)
         self._stage = [(torch.zeros_like(self.x), torch.zeros_like(self.y)) for _ in range(2)]
@@ -69,20 +136,115 @@ class TrainStep:
         self._warm = 0
 
     # -- pieces ------------------------------------------------------------------------------------------
+    def _reduce_early(self):
+        """Called by the encoder GRU's backward bridge once its parameter-gradient kernels have been issued: every
+        gradient of the early group is now in flight on the parameter side streams."""
+        dev = self.x.device
+        cs = self._comm_stream
+        cs.wait_stream(torch.cuda.current_stream(dev))
+        for st in F._param_stream_list(dev):
+            cs.wait_stream(st)
+        with torch.cuda.stream(cs):
+            dist.all_reduce(self.bucket.early, op=dist.ReduceOp.AVG)
+        self._early_work = cs
+
     def _fwd_bwd(self):
         self.opt.zero_grad(set_to_none=True)
-        preds, recons = self.model(self.x)
-        fl, rl = rmse_losses(self.x, self.y, preds, recons, self.target_dims)
-        (fl + rl).backward()
+        dev = self.x.device
+        hooked = self.bucket is not None
+        if hooked:
+            F._grad_sinks[dev] = self.bucket.sinks
+            if self.overlap_comm and self.pipeline == 1:
+                F._after_encoder_bwd[dev] = self._reduce_early
+        self._early_work = None
+        try:
+            if self.pipeline == 1:
+                preds, recons = self.model(self.x)
+            else:
+                preds, recons = self._forward_pipelined()
+            fl, rl = rmse_losses(self.x, self.y, preds, recons, self.target_dims)
+            (fl + rl).backward()
+            if self.pipeline > 1:
+                main = [p.grad for p in self.params]
+                for al in self._alias:
+                    torch._foreach_add_(main, [al[nm].grad for nm in self._names])
+        finally:
+            if hooked:
+                F._grad_sinks.pop(dev, None)
+                F._after_encoder_bwd.pop(dev, None)
         self.losses[0].copy_(fl.detach())
         self.losses[1].copy_(rl.detach())
 
+    def _forward_pipelined(self):
+        cur = torch.cuda.current_stream(self.x.device)
+        B = self.x.shape[0]
+        per = (B // self.pipeline + 15) // 16 * 16
+        outs = []
+        for i, st in enumerate(self._pipe_streams):
+            lo, hi = i * per, (B if i == self.pipeline - 1 else (i + 1) * per)
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                xi = self.x[lo:hi]
+                if i == 0:
+                    o = self.model(xi)
+                else:
+                    for a in self._alias[i - 1].values():
+                        a.grad = None
+                    o = torch.func.functional_call(self.model, self._alias[i - 1], (xi,))
+            outs.append(o)
+        for st, o in zip(self._pipe_streams, outs):
+            cur.wait_stream(st)
+            o[0].record_stream(cur); o[1].record_stream(cur)
+        return torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+
     def _allreduce(self):
-        allreduce_gradients(self.params, self.world)
+        if self.world == 1:
+            return
+        if self.bucket is None or not self.bucket.adopted():
+            allreduce_gradients(self.params, self.world)          # generic path (gloo, or views not adopted)
+            if self._early_work is not None:
+                torch.cuda.current_stream().wait_stream(self._early_work)
+            return
+        if self._early_work is None:
+            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(self.bucket.late, op=dist.ReduceOp.AVG)
+            torch.cuda.current_stream().wait_stream(self._early_work)
+
+    def _snapshot(self):
+        seed = F.seed_state(self.x.device)
+        return ([p.detach().clone() for p in self.params],
+                {id(p): {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.opt.state.get(p, {}).items()}
+                 for p in self.params},
+                None if seed is None else seed.clone())
+
+    def _restore(self, snap):
+        """Undo the warm-up steps IN PLACE (a capture holds the addresses of parameters, optimizer state and seed)."""
+        ps, st, seed = snap
+        with torch.no_grad():
+            for p, q in zip(self.params, ps):
+                p.copy_(q)
+            for p in self.params:
+                cur, old = self.opt.state.get(p, {}), st[id(p)]
+                for k, v in cur.items():
+                    if torch.is_tensor(v):
+                        if k in old:
+                            v.copy_(old[k])
+                        else:
+                            v.zero_()                     # state created by the warm-up: back to its initial value
+            now = F.seed_state(self.x.device)
+            if now is not None:
+                if seed is not None:
+                    now.copy_(seed)
+                elif self._seed0 is not None:
+                    now.fill_(self._seed0)
 
     def _capture(self):
         # warm-up and capture on the SAME stream: the library's GEMM pack workspaces are per stream and cannot grow
-        # during capture (include/mtadgat.h: mtadgat_workspace_reserve)
+        # during capture (include/mtadgat.h: mtadgat_workspace_reserve).  The warm-up steps are undone afterwards:
+        # the first run_* call performs exactly one optimisation step.
+        self._seed0 = torch.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        snap = self._snapshot()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -90,11 +252,15 @@ class TrainStep:
                 self._fwd_bwd(); self._allreduce(); self.opt.step()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self._restore(snap)
+        torch.cuda.synchronize()
         F.reset_launch_count()
-        if self.world == 1:
+        one_graph = self.world == 1 or (self.capture_comm and self.bucket is not None)
+        if one_graph:
             self.g_fb = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.g_fb, stream=s):
                 self._fwd_bwd()
+                self._allreduce()
                 self.opt.step()
         else:
             self.g_fb = torch.cuda.CUDAGraph()
@@ -112,7 +278,7 @@ class TrainStep:
         if self.g_fb is None:
             self._capture()
         self.g_fb.replay()
-        if self.world > 1:
+        if self.g_opt is not None:
             self._allreduce()
             self.g_opt.replay()
 

@@ -1,0 +1,94 @@
+"""Test-side helpers around the numpy oracle (oracle/mtad_gat_oracle.py): chunked evaluation at the benchmark's
+batch size, the Philox masks the kernels draw, and a numpy Adam.  Test infrastructure only."""
+import numpy as np
+import torch
+
+from oracle import mtad_gat_oracle as orc
+
+SEED_STEP = 0x9E3779B97F4A7C15          # seed_advance_kernel (csrc/api.cu): one splitmix64 increment per forward
+MASK64 = (1 << 64) - 1
+
+
+def _slice_masks(masks, lo, hi):
+    if not masks:
+        return None
+    out = {}
+    for key, v in masks.items():
+        out[key] = [m[lo:hi] for m in v] if isinstance(v, list) else v[lo:hi]
+    return out
+
+
+def loss_fwd_bwd_chunked(x, y, params, cfg, masks=None, target_dims=None, chunk=32):
+    """orc.loss_fwd_bwd for batches whose materialised (B,K,K,2D) tensors do not fit at once: windows are independent
+    up to the two global sqrt(MSE) normalisers, so forward in chunks, form the losses, then forward+backward in chunks
+    with the chunk's slice of dL/dpreds, dL/drecons and sum the parameter gradients.
+    Returns (loss, lf, lr, preds, recons, dx, grads) like orc.loss_fwd_bwd."""
+    B = x.shape[0]
+    preds, recons = [], []
+    for lo in range(0, B, chunk):
+        p, r, _ = orc.model_fwd(x[lo:lo + chunk], params, cfg, _slice_masks(masks, lo, lo + chunk))
+        preds.append(p); recons.append(r)
+    preds, recons = np.concatenate(preds), np.concatenate(recons)
+    xt = x if target_dims is None else x[:, :, target_dims]
+    yt = y if target_dims is None else y[:, :, target_dims]
+    yt = yt.reshape(B, -1)
+    lf, lr = np.sqrt(((yt - preds) ** 2).mean()), np.sqrt(((xt - recons) ** 2).mean())
+    dpreds = (preds - yt) / (preds.size * lf)
+    drecons = (recons - xt) / (recons.size * lr)
+    dx = np.zeros_like(x)
+    grads = None
+    for lo in range(0, B, chunk):
+        hi = min(B, lo + chunk)
+        _, _, cache = orc.model_fwd(x[lo:hi], params, cfg, _slice_masks(masks, lo, hi))
+        dxi, gi = orc.model_bwd(dpreds[lo:hi], drecons[lo:hi], cache, params, cfg)
+        dx[lo:hi] = dxi
+        if grads is None:
+            grads = {k: v.copy() for k, v in gi.items()}
+        else:
+            for k, v in gi.items():
+                grads[k] += v
+    direct = (xt - recons) / (recons.size * lr)            # x is also the reconstruction target
+    if target_dims is None:
+        dx += direct
+    else:
+        dx[:, :, target_dims] += direct
+    return lf + lr, lf, lr, preds, recons, dx, grads
+
+
+def seed_after(seed0, n_forwards):
+    """Value of the device seed after `n_forwards` training-mode forwards starting from manual_seed(seed0)."""
+    return (int(seed0) + n_forwards * SEED_STEP) & MASK64
+
+
+def masks_for_seed(seed_value, cfg, B, p, device="cuda"):
+    """The dropout multipliers MTAD_GAT.forward applies under the given per-step seed, via mtadgat_dropout_mask
+    (same Philox stream ids as the kernels), as float64 numpy arrays in the oracle's mask format."""
+    from mtad_gat_pytorch_b200 import functional as F
+    v = seed_value & MASK64
+    if v >= 1 << 63:
+        v -= 1 << 64
+    st = torch.tensor([v], dtype=torch.int64, device=device)
+
+    def m(numel, stream, shape):
+        return F.dropout_multipliers(numel, p, st, stream).view(*shape).cpu().numpy().astype(np.float64)
+    return {"feat": m(B * cfg.k * cfg.k, F.RNG_FEATURE, (B, cfg.k, cfg.k)),
+            "temp": m(B * cfg.n * cfg.n, F.RNG_TEMPORAL, (B, cfg.n, cfg.n)),
+            "mlp": [m(B * cfg.forecast_hid_dim, F.RNG_MLP0 + i, (B, cfg.forecast_hid_dim))
+                    for i in range(cfg.forecast_n_layers)]}
+
+
+class NumpyAdam:
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0) on a dict of numpy arrays."""
+
+    def __init__(self, params, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+        self.p, self.lr, self.b1, self.b2, self.eps, self.t = params, lr, b1, b2, eps, 0
+        self.m = {k: np.zeros_like(v) for k, v in params.items()}
+        self.v = {k: np.zeros_like(v) for k, v in params.items()}
+
+    def step(self, grads):
+        self.t += 1
+        c1, c2 = 1 - self.b1 ** self.t, 1 - self.b2 ** self.t
+        for k, g in grads.items():
+            self.m[k] = self.b1 * self.m[k] + (1 - self.b1) * g
+            self.v[k] = self.b2 * self.v[k] + (1 - self.b2) * g * g
+            self.p[k] = self.p[k] - (self.lr / c1) * self.m[k] / (np.sqrt(self.v[k]) / np.sqrt(c2) + self.eps)
