@@ -101,6 +101,28 @@ def load_reference():
     return mod.MTAD_GAT
 
 
+def calibrate_threads(cfgname, gatv1=False):
+    """The reference's CPU path at this shape is dominated by page-faulting multi-GB temporaries: on a 128-thread host it
+    runs several times SLOWER with all threads than with a few.  The baseline should be the reference at its best, so
+    one short step at a reduced batch is timed per candidate thread count and the fastest is used (reported as `cores`)."""
+    import torch
+    n_all = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, n_all) if c <= n_all})
+    rb = max(2, min(32, CONFIGS[cfgname]["ref_batch"]))
+    best = (None, 0.0)
+    tried = {}
+    for c in cands:
+        torch.set_num_threads(c)
+        res = reference_rate(cfgname, rb, 1, 1, "cpu", gatv1, budget_s=30.0)
+        if res is None:
+            return n_all, {}
+        tried[c] = round(res[0], 1)
+        if res[0] > best[1]:
+            best = (c, res[0])
+    torch.set_num_threads(best[0])
+    return best[0], tried
+
+
 def reference_rate(cfgname, batch, steps, warmup, device, gatv1=False, budget_s=150.0):
     """windows/s of the reference's own step (training.py:109-127: zero_grad, forward, sqrt-MSE losses, backward,
     Adam.step) or no_grad forward (prediction.py:50-55), fp32, on `device`.  Returns (mean_rate, best_rate, times_s)."""
@@ -198,8 +220,7 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
+    cores, tried = calibrate_threads(args.config, args.gatv1)
     c = CONFIGS[args.config]
     rb = c["ref_batch"]
     res = reference_rate(args.config, rb, max(1, args.steps), max(1, min(args.warmup, 2)), "cpu", args.gatv1)
@@ -211,7 +232,8 @@ def run_reference(args):
     mean, best, times = res
     ms = 1e3 * sum(times) / len(times)
     sample = (f"{len(times)} timed steps of the unmodified reference (baseline/_ref mtad_gat.py + modules.py, torch "
-              f"{torch.__version__} CPU, {cores} threads, fp32) at batch {rb}" if kind == "reference" else
+              f"{torch.__version__} CPU, fp32) at batch {rb} with {cores} of {os.cpu_count()} host threads -- the fastest of "
+              f"the calibrated counts {tried} (windows/s at a reduced batch)" if kind == "reference" else
               f"{len(times)} timed {rb}-window fwd+bwd passes of the numpy port (oracle/): baseline/_ref was not staged")
     line = {
         "impl": "reference", "metric": metric_name(args.config), "value": mean, "unit": "windows/s",
@@ -530,14 +552,14 @@ def run_ours(args):
         cpu = None
         ref_cuda = None
         if world == 1 and not args.skip_cpu:
-            torch.set_num_threads(os.cpu_count())
-            res = reference_rate(args.config, c["ref_batch"], 3 if c["ref_batch"] >= 64 else 2, 1, "cpu", args.gatv1)
+            cores, tried = calibrate_threads(args.config, args.gatv1)
+            res = reference_rate(args.config, c["ref_batch"], 3 if c["ref_batch"] >= 64 else 2, 1, "cpu", args.gatv1, budget_s=60.0)
             if res is not None:
                 mean, best, times = res
-                cpu = {"value": mean, "best": best, "unit": "windows/s", "cores": os.cpu_count(), "kind": "reference",
-                       "cpu": cpu_model_name(),
+                cpu = {"value": mean, "best": best, "unit": "windows/s", "cores": cores, "kind": "reference",
+                       "cpu": cpu_model_name(), "host_threads": os.cpu_count(), "threads_calibration": tried,
                        "sample": f"{len(times)} timed steps (after 1 warm-up) of the unmodified reference (baseline/_ref, torch CPU "
-                                 f"fp32, {os.cpu_count()} threads) at batch {c['ref_batch']} ({sum(times):.1f} s)"}
+                                 f"fp32, {cores} threads = fastest calibrated count) at batch {c['ref_batch']} ({sum(times):.1f} s)"}
             else:
                 mean, best, times = oracle_port_rate(args.config, 16, 3)
                 cpu = {"value": mean, "unit": "windows/s", "cores": os.cpu_count(), "kind": "port",

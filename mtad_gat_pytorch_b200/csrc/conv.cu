@@ -178,7 +178,7 @@ extern "C" int mtadgat_conv_relu_fwd(const float* x, const float* w, const float
   ConvShiftLoad<false> A{x, nullptr, n, k, (ks - 1) / 2, +1, nullptr, nullptr};
   ConvWFwd Bw{w, k, ks};
   StStrided C{y, 0, k, 1, bias, ACT_RELU, 0};
-  launch_gemm_batched(1, B * n, k, ks * k, A, Bw, C, s);
+  launch_gemm_batched_precise(1, B * n, k, ks * k, A, Bw, C, s);      // feeds the ReLU gate (backward tests y > 0)
   MG_CHECK_LAUNCH("conv_relu_fwd");
   return MTADGAT_OK;
 }

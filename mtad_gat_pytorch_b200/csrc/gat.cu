@@ -1206,8 +1206,9 @@ extern "C" int mtadgat_gat_fwd(const float* x, const float* lin_w, const float* 
   {
     WpT A{wp, d.NC};
     StPQt C{pqt, bp, d.NC, d.Kp};
-    if (feature) launch_gemm_batched(B, d.NC, d.K, d.D, A, NodeB<true>{x, n, k}, C, s);
-    else launch_gemm_batched(B, d.NC, d.K, d.D, A, NodeB<false>{x, n, k}, C, s);
+    // P, Q feed the LeakyReLU slope decision (P_id + Q_jd > 0) of K*K*E score elements per window: three-term operands
+    if (feature) launch_gemm_batched_precise(B, d.NC, d.K, d.D, A, NodeB<true>{x, n, k}, C, s);
+    else launch_gemm_batched_precise(B, d.NC, d.K, d.D, A, NodeB<false>{x, n, k}, C, s);
   }
   int RB = 0, JT = 0, DT = 0; size_t smem = 0;
   const bool win = d.K <= 128 && score_win_smem(d) <= 112 * 1024;    // whole-window CTA, two resident per SM

@@ -148,6 +148,16 @@ static inline void launch_gemm_batched(int batch, int M, int N, int K, AL A, BL 
   MG_COUNT_LAUNCH();
 }
 
+// Same product for a GEMM whose output feeds a discontinuous gate (ReLU / LeakyReLU slope): the tensor-core path splits
+// the operands into three bf16 terms (six products, fp32-level accuracy) so that gate decisions agree with an fp32
+// evaluation except on a set of measure ~1e-7 instead of ~1e-5 (tc_gemm2.cuh).
+template <class AL, class BL, class CS>
+static inline void launch_gemm_batched_precise(int batch, int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s) {
+  if (M <= 0 || N <= 0 || batch <= 0) return;
+  if (g_mtadgat_gemm_impl == 1 && N >= 16 && K >= 16) { tcg2::launch_batched_precise(batch, M, N, K, A, Bm, C, s); return; }
+  launch_gemm_batched(batch, M, N, K, A, Bm, C, s);
+}
+
 // Split-K: C must be zero-initialised by the caller (cudaMemsetAsync); bias/act are ignored.
 // sumA / sumB (nullable, zero-initialised by the caller): sumA[m] += sum_k A(m,k), sumB[n] += sum_k B(k,n).  Returns true
 // when the sums were produced (packed-operand path); false = the caller must run its own column-sum kernel.

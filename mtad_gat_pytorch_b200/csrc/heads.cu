@@ -39,8 +39,11 @@ extern "C" int mtadgat_linear_fwd(const float* x, const float* w, const float* b
   MG_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || seed), "linear_fwd: bad dropout arguments");
   cudaStream_t s = (cudaStream_t)stream;
   // A(m,kk) = x[m*I+kk] ; B(kk, o) = w[o*I + kk]
-  launch_gemm_batched(1, M, O, I, Strided2<true>{x, 0, I, 1}, Strided2<false>{w, 0, 1, I},
-                      StLinear{y, O, b, act, p_drop, 1.f / (1.f - p_drop), seed, rng_stream}, s);
+  const StLinear C{y, O, b, act, p_drop, 1.f / (1.f - p_drop), seed, rng_stream};
+  if (act == ACT_RELU)     // the backward's gate is y > 0: three-term operands in front of it
+    launch_gemm_batched_precise(1, M, O, I, Strided2<true>{x, 0, I, 1}, Strided2<false>{w, 0, 1, I}, C, s);
+  else
+    launch_gemm_batched(1, M, O, I, Strided2<true>{x, 0, I, 1}, Strided2<false>{w, 0, 1, I}, C, s);
   MG_CHECK_LAUNCH("linear_fwd");
   return MTADGAT_OK;
 }

@@ -22,7 +22,32 @@ void mtadgat_set_pending_error(int rc);
 namespace tcg2 {
 
 constexpr int BM = 128, BK = 32, KG = BK / 8, NTHREADS = 256, STAGES = 3;
-template <int R> struct Tile { static constexpr int HALF = KG * R * 16, BYTES = 2 * HALF; };   // hi block, lo block
+// NS = number of bf16 terms an fp32 operand value is split into: 2 (hi, lo: "bf16x3", three products, ~1e-5 relative --
+// the default) or 3 (hi, lo, lo2: six products, fp32-level accuracy).  The 3-term form is used by the FORWARD GEMMs whose
+// outputs feed a discontinuous gate (conv -> ReLU, GAT projections -> LeakyReLU slope, MLP -> ReLU): with ~1e-5 errors a
+// few hundred of the ~3e8 gate pre-activations of a 256-window step sit close enough to zero to take the other branch,
+// and each such flip is a 1e-3..1e-2 blip in that window's gradients against an fp64 evaluation.
+template <int R, int NS = 2> struct Tile { static constexpr int HALF = KG * R * 16, BYTES = NS * HALF; };   // term blocks
+
+// 8 fp32 values -> three bf16 terms (hi = rn(x), lo = rn(x - hi), lo2 = rn(x - hi - lo)), one 16-byte K group each
+__device__ __forceinline__ void store_split8_3(uint8_t* b0, uint8_t* b1, uint8_t* b2, uint32_t off, const float (&v)[8]) {
+  uint32_t h[4], l[4], m[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    float2 hf = __bfloat1622float2(hh);
+    const float r0 = v[2 * j] - hf.x, r1 = v[2 * j + 1] - hf.y;
+    __nv_bfloat162 ll = __floats2bfloat162_rn(r0, r1);
+    float2 lf = __bfloat1622float2(ll);
+    __nv_bfloat162 mm = __floats2bfloat162_rn(r0 - lf.x, r1 - lf.y);
+    h[j] = *reinterpret_cast<uint32_t*>(&hh);
+    l[j] = *reinterpret_cast<uint32_t*>(&ll);
+    m[j] = *reinterpret_cast<uint32_t*>(&mm);
+  }
+  *reinterpret_cast<uint4*>(b0 + off) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(b1 + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  *reinterpret_cast<uint4*>(b2 + off) = make_uint4(m[0], m[1], m[2], m[3]);
+}
 
 // store functors whose output is contiguous along n (row-major C) get a transposed epilogue: the accumulator chunk
 // goes through shared memory so that a warp writes 128 contiguous bytes per row instead of 32 scattered words.
@@ -33,7 +58,7 @@ template <class F> struct BatchInvariant { static constexpr bool value = false; 
 
 // linesum (nullable): linesum[l] += sum_k operand(l, k) -- the bias gradients of the path are exactly the line sums of a
 // weight-gradient GEMM operand, so they ride along with the pack instead of costing a column-sum kernel
-template <class Op, class F, int R>
+template <class Op, class F, int R, int NS>
 __device__ __forceinline__ void pack_row(const F& f, int z, int L, int K, int ltile, int ktile, int row, uint8_t* tile,
                                          float* __restrict__ linesum) {
   const int l = ltile * R + row;
@@ -46,7 +71,8 @@ __device__ __forceinline__ void pack_row(const F& f, int z, int L, int K, int lt
     for (int g = 0; g < KG; ++g) {
       float v[8];
       Op::load8(f, ctx, z, ktile * BK + g * 8, K, v);
-      tcg::store_split8(hi, lo, (uint32_t)(g * R + row) * 16, v);
+      if (NS == 3) store_split8_3(hi, lo, lo + Tile<R>::HALF, (uint32_t)(g * R + row) * 16, v);
+      else tcg::store_split8(hi, lo, (uint32_t)(g * R + row) * 16, v);
       acc += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
     }
     if (linesum) atomicAdd(linesum + l, acc);
@@ -57,7 +83,7 @@ __device__ __forceinline__ void pack_row(const F& f, int z, int L, int K, int lt
 
 // one thread per (z, line tile, k tile, row): 32 consecutive K of one operand line -> 4 hi + 4 lo 16-byte groups.
 // Threads [0, nA) pack A, the rest pack B (both counts are multiples of 32: warps never straddle).
-template <class AL, class BL, int BN>
+template <class AL, class BL, int BN, int NS>
 __global__ void __launch_bounds__(256) pack_kernel(AL A, BL Bm, int M, int N, int K, int KT, int MT, int NT, int nzA,
                                                    int nzB, uint8_t* __restrict__ Ap, uint8_t* __restrict__ Bp,
                                                    float* __restrict__ sumA, float* __restrict__ sumB) {
@@ -68,14 +94,14 @@ __global__ void __launch_bounds__(256) pack_kernel(AL A, BL Bm, int M, int N, in
     long long tile = g / BM;
     const int ktile = (int)(tile % KT);
     const long long t2 = tile / KT;
-    pack_row<tcg::OpA<AL>, AL, BM>(A, (int)(t2 / MT), M, K, (int)(t2 % MT), ktile, row, Ap + tile * Tile<BM>::BYTES, sumA);
+    pack_row<tcg::OpA<AL>, AL, BM, NS>(A, (int)(t2 / MT), M, K, (int)(t2 % MT), ktile, row, Ap + tile * Tile<BM, NS>::BYTES, sumA);
   } else if (g - nA < nB) {
     g -= nA;
     const int row = (int)(g % BN);
     long long tile = g / BN;
     const int ktile = (int)(tile % KT);
     const long long t2 = tile / KT;
-    pack_row<tcg::OpB<BL>, BL, BN>(Bm, (int)(t2 / NT), N, K, (int)(t2 % NT), ktile, row, Bp + tile * Tile<BN>::BYTES, sumB);
+    pack_row<tcg::OpB<BL>, BL, BN, NS>(Bm, (int)(t2 / NT), N, K, (int)(t2 % NT), ktile, row, Bp + tile * Tile<BN, NS>::BYTES, sumB);
   }
 }
 
@@ -87,18 +113,20 @@ __device__ __forceinline__ void arrive_expect_tx(uint64_t* bar, uint32_t bytes) 
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-template <int BN> struct Smem2 {
-  static constexpr int STAGE = Tile<BM>::BYTES + Tile<BN>::BYTES;
+template <int BN, int NS = 2> struct Smem2 {
+  static constexpr int STAGE = Tile<BM, NS>::BYTES + Tile<BN, NS>::BYTES;
   static constexpr int TOTAL = STAGES * STAGE + 128;
 };
 
 // C(z,m,n) = sum_k A(z,m,k) B(z,k,n) from packed operands; batch / split-K semantics as gemm_kernel (split-K over
 // whole k-tiles: blockIdx.z owns k-tiles [z*kt_len, (z+1)*kt_len))
-template <class CS, int BN>
+template <class CS, int BN, int NS>
 __global__ void __launch_bounds__(NTHREADS) gemm2_kernel(const uint8_t* __restrict__ Ap, const uint8_t* __restrict__ Bp,
                                                          int M, int N, int KT, int kt_len, int splitk, int MT, int NT,
                                                          int zA, int zB, CS C) {
-  using S = Smem2<BN>;
+  using S = Smem2<BN, NS>;
+  using TA = Tile<BM, NS>;
+  using TB = Tile<BN, NS>;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + STAGES * S::STAGE);   // [STAGES] tile landed
   uint64_t* empty = full + STAGES;                                              // [STAGES] MMAs that read it are done
@@ -133,22 +161,22 @@ __global__ void __launch_bounds__(NTHREADS) gemm2_kernel(const uint8_t* __restri
   if (warp == 0) {
     // ---- producer: one lane streams the packed tiles of this CTA's (m tile, n tile) ----
     if (lane == 0 && nkt > 0) {
-      const uint8_t* a_src = Ap + ((size_t)((zA ? z : 0) * MT + mt) * KT + kt0) * Tile<BM>::BYTES;
-      const uint8_t* b_src = Bp + ((size_t)((zB ? z : 0) * NT + nt) * KT + kt0) * Tile<BN>::BYTES;
+      const uint8_t* a_src = Ap + ((size_t)((zA ? z : 0) * MT + mt) * KT + kt0) * TA::BYTES;
+      const uint8_t* b_src = Bp + ((size_t)((zB ? z : 0) * NT + nt) * KT + kt0) * TB::BYTES;
       for (int i = 0; i < nkt; ++i) {
         const int s = i % STAGES;
         if (i >= STAGES) tc::mbar_wait(empty + s, ((i / STAGES) - 1) & 1);
-        arrive_expect_tx(full + s, (uint32_t)(2 * KG * 16 * (rowsA + rowsB)));
-        const uint32_t sa = sbase + (uint32_t)(s * S::STAGE), sb = sa + Tile<BM>::BYTES;
-        const uint8_t* ga = a_src + (size_t)i * Tile<BM>::BYTES;
-        const uint8_t* gb = b_src + (size_t)i * Tile<BN>::BYTES;
-        if (rowsA == BM) bulk_g2s(sa, ga, Tile<BM>::BYTES, full + s);
+        arrive_expect_tx(full + s, (uint32_t)(NS * KG * 16 * (rowsA + rowsB)));
+        const uint32_t sa = sbase + (uint32_t)(s * S::STAGE), sb = sa + TA::BYTES;
+        const uint8_t* ga = a_src + (size_t)i * TA::BYTES;
+        const uint8_t* gb = b_src + (size_t)i * TB::BYTES;
+        if (rowsA == BM) bulk_g2s(sa, ga, TA::BYTES, full + s);
         else
-          for (int g = 0; g < 2 * KG; ++g)        // one copy per (hi|lo, k group): the live rows are contiguous there
+          for (int g = 0; g < NS * KG; ++g)       // one copy per (term, k group): the live rows are contiguous there
             bulk_g2s(sa + (uint32_t)(g * BM * 16), ga + (size_t)g * BM * 16, (uint32_t)rowsA * 16, full + s);
-        if (rowsB == BN) bulk_g2s(sb, gb, Tile<BN>::BYTES, full + s);
+        if (rowsB == BN) bulk_g2s(sb, gb, TB::BYTES, full + s);
         else
-          for (int g = 0; g < 2 * KG; ++g)
+          for (int g = 0; g < NS * KG; ++g)
             bulk_g2s(sb + (uint32_t)(g * BN * 16), gb + (size_t)g * BN * 16, (uint32_t)rowsB * 16, full + s);
       }
     }
@@ -159,15 +187,26 @@ __global__ void __launch_bounds__(NTHREADS) gemm2_kernel(const uint8_t* __restri
       const int s = i % STAGES;
       tc::mbar_wait(full + s, (i / STAGES) & 1);
       tc::tc_fence_after();
-      const uint32_t a0 = sbase + (uint32_t)(s * S::STAGE), b0 = a0 + Tile<BM>::BYTES;
+      const uint32_t a0 = sbase + (uint32_t)(s * S::STAGE), b0 = a0 + TA::BYTES;
 #pragma unroll
       for (int j = 0; j < BK / 16; ++j) {
         const uint32_t ao = (uint32_t)(2 * j) * BM * 16, bo = (uint32_t)(2 * j) * BN * 16;
         const uint64_t dAh = tc::make_smem_desc(a0 + ao, BM * 16, 128);
-        const uint64_t dAl = tc::make_smem_desc(a0 + Tile<BM>::HALF + ao, BM * 16, 128);
+        const uint64_t dAl = tc::make_smem_desc(a0 + TA::HALF + ao, BM * 16, 128);
         const uint64_t dBh = tc::make_smem_desc(b0 + bo, BN * 16, 128);
-        const uint64_t dBl = tc::make_smem_desc(b0 + Tile<BN>::HALF + bo, BN * 16, 128);
-        if (tc::elect_one()) {
+        const uint64_t dBl = tc::make_smem_desc(b0 + TB::HALF + bo, BN * 16, 128);
+        if (NS == 3) {
+          const uint64_t dAm = tc::make_smem_desc(a0 + 2 * TA::HALF + ao, BM * 16, 128);
+          const uint64_t dBm = tc::make_smem_desc(b0 + 2 * TB::HALF + bo, BN * 16, 128);
+          if (tc::elect_one()) {                                                 // smallest terms first
+            tc::mma_f16_ss(tbase, dAl, dBl, idesc, (i > 0 || j > 0) ? 1u : 0u);
+            tc::mma_f16_ss(tbase, dAm, dBh, idesc, 1u);
+            tc::mma_f16_ss(tbase, dAh, dBm, idesc, 1u);
+            tc::mma_f16_ss(tbase, dAl, dBh, idesc, 1u);
+            tc::mma_f16_ss(tbase, dAh, dBl, idesc, 1u);
+            tc::mma_f16_ss(tbase, dAh, dBh, idesc, 1u);
+          }
+        } else if (tc::elect_one()) {
           tc::mma_f16_ss(tbase, dAl, dBh, idesc, (i > 0 || j > 0) ? 1u : 0u);   // small terms first
           tc::mma_f16_ss(tbase, dAh, dBl, idesc, 1u);
           tc::mma_f16_ss(tbase, dAh, dBh, idesc, 1u);
@@ -227,23 +266,23 @@ __global__ void __launch_bounds__(NTHREADS) gemm2_kernel(const uint8_t* __restri
   if (warp == 0) tc::tmem_dealloc(tbase, BN);
 }
 
-template <class AL, class BL, class CS, int BN>
+template <class AL, class BL, class CS, int BN, int NS = 2>
 static inline int run(int batch, int M, int N, int K, int splits_wanted, bool splitk, AL A, BL Bm, CS C, cudaStream_t s,
                       float* sumA = nullptr, float* sumB = nullptr) {
   const int KT = cdiv(K, BK), MT = cdiv(M, BM), NT = cdiv(N, BN);
   const int nzA = (!splitk && !BatchInvariant<AL>::value) ? batch : 1;
   const int nzB = (!splitk && !BatchInvariant<BL>::value) ? batch : 1;
-  const size_t a_bytes = (size_t)nzA * MT * KT * Tile<BM>::BYTES, b_bytes = (size_t)nzB * NT * KT * Tile<BN>::BYTES;
+  const size_t a_bytes = (size_t)nzA * MT * KT * Tile<BM, NS>::BYTES, b_bytes = (size_t)nzB * NT * KT * Tile<BN, NS>::BYTES;
   uint8_t* ws = mtadgat_workspace(s, a_bytes + b_bytes);
   if (!ws) { mtadgat_set_pending_error(MTADGAT_ERR_CUDA); return MTADGAT_ERR_CUDA; }
   uint8_t* Ap = ws; uint8_t* Bp = ws + a_bytes;
   const long long nthreads = (long long)nzA * MT * KT * BM + (long long)nzB * NT * KT * BN;
-  pack_kernel<AL, BL, BN><<<cdiv(nthreads, 256), 256, 0, s>>>(A, Bm, M, N, K, KT, MT, NT, nzA, nzB, Ap, Bp, sumA, sumB);
+  pack_kernel<AL, BL, BN, NS><<<cdiv(nthreads, 256), 256, 0, s>>>(A, Bm, M, N, K, KT, MT, NT, nzA, nzB, Ap, Bp, sumA, sumB);
   MG_COUNT_LAUNCH();
-  constexpr int smem = Smem2<BN>::TOTAL;
+  constexpr int smem = Smem2<BN, NS>::TOTAL;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gemm2_kernel<CS, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(gemm2_kernel<CS, BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured = true;
   }
   int kt_len = KT, nz = batch;
@@ -252,7 +291,7 @@ static inline int run(int batch, int M, int N, int K, int splits_wanted, bool sp
     kt_len = cdiv(KT, splits);
     nz = cdiv(KT, kt_len);
   }
-  gemm2_kernel<CS, BN><<<dim3(NT, MT, nz), NTHREADS, smem, s>>>(Ap, Bp, M, N, KT, kt_len, splitk ? 1 : 0, MT, NT,
+  gemm2_kernel<CS, BN, NS><<<dim3(NT, MT, nz), NTHREADS, smem, s>>>(Ap, Bp, M, N, KT, kt_len, splitk ? 1 : 0, MT, NT,
                                                                nzA > 1 ? 1 : 0, nzB > 1 ? 1 : 0, C);
   MG_COUNT_LAUNCH();
   return MTADGAT_OK;
@@ -262,6 +301,12 @@ template <class AL, class BL, class CS>
 static inline int launch_batched(int batch, int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s) {
   if (N <= 64) return run<AL, BL, CS, 64>(batch, M, N, K, 1, false, A, Bm, C, s);
   return run<AL, BL, CS, 128>(batch, M, N, K, 1, false, A, Bm, C, s);
+}
+// three-term operands (fp32-level accuracy): for the forward GEMMs in front of a ReLU / LeakyReLU gate
+template <class AL, class BL, class CS>
+static inline int launch_batched_precise(int batch, int M, int N, int K, AL A, BL Bm, CS C, cudaStream_t s) {
+  if (N <= 64) return run<AL, BL, CS, 64, 3>(batch, M, N, K, 1, false, A, Bm, C, s);
+  return run<AL, BL, CS, 128, 3>(batch, M, N, K, 1, false, A, Bm, C, s);
 }
 
 template <class AL, class BL, class CS>

@@ -186,6 +186,9 @@ class Forecasting_Model(nn.Module, _SeedMixin):
     def forward(self, x):
         p = self.dropout.p if self.training else 0.0
         seed = self._seed(x.device, p)
+        rec = getattr(self, "_gate_record", None)       # tests: a list collects (activation > 0) per hidden layer
         for i in range(len(self.layers) - 1):
             x = F.LinearFn.apply(x, self.layers[i].weight, self.layers[i].bias, 1, p, seed, F.RNG_MLP0 + i)
+            if rec is not None:
+                rec.append(x.detach() > 0)
         return F.LinearFn.apply(x, self.layers[-1].weight, self.layers[-1].bias, 0, 0.0, None, 0)

@@ -8,11 +8,12 @@ from mtad_gat_pytorch_b200 import training as mgt
 from torch.profiler import profile, ProfilerActivity
 split = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 if split: mg.set_gru_split(split)
+pipes = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 B = 256
 torch.manual_seed(0)
 m = mg.MTAD_GAT(38, 100, 38, forecast_n_layers=3, dropout=0.3).cuda().train()
 opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True, fused=True)
-step = mgt.TrainStep(m, opt, batch=B, use_graph=True, world_size=1)
+step = mgt.TrainStep(m, opt, batch=B, use_graph=True, world_size=1, pipeline=pipes)
 x = torch.rand(B, 100, 38, device="cuda"); y = torch.rand(B, 1, 38, device="cuda")
 for _ in range(5): step.run_device(x, y)
 torch.cuda.synchronize()

@@ -24,11 +24,12 @@ def loss_fwd_bwd_chunked(x, y, params, cfg, masks=None, target_dims=None, chunk=
     with the chunk's slice of dL/dpreds, dL/drecons and sum the parameter gradients.
     Returns (loss, lf, lr, preds, recons, dx, grads) like orc.loss_fwd_bwd."""
     B = x.shape[0]
-    preds, recons = [], []
+    preds, recons, pres = [], [], []
     for lo in range(0, B, chunk):
-        p, r, _ = orc.model_fwd(x[lo:lo + chunk], params, cfg, _slice_masks(masks, lo, lo + chunk))
-        preds.append(p); recons.append(r)
+        p, r, cache = orc.model_fwd(x[lo:lo + chunk], params, cfg, _slice_masks(masks, lo, lo + chunk))
+        preds.append(p); recons.append(r); pres.append(cache[4][4])
     preds, recons = np.concatenate(preds), np.concatenate(recons)
+    loss_fwd_bwd_chunked.last_mlp_pre = [np.concatenate([c[i] for c in pres]) for i in range(len(pres[0]))]
     xt = x if target_dims is None else x[:, :, target_dims]
     yt = y if target_dims is None else y[:, :, target_dims]
     yt = yt.reshape(B, -1)
@@ -92,3 +93,31 @@ class NumpyAdam:
             self.m[k] = self.b1 * self.m[k] + (1 - self.b1) * g
             self.v[k] = self.b2 * self.v[k] + (1 - self.b2) * g * g
             self.p[k] = self.p[k] - (self.lr / c1) * self.m[k] / (np.sqrt(self.v[k]) / np.sqrt(c2) + self.eps)
+
+
+def align_mlp_gates(gpu_gates, masks, x, params, cfg, tol=1e-3):
+    """ReLU-branch bookkeeping for the forecasting head (see orc.forecast_fwd): `gpu_gates` = the implementation's
+    (activation > 0) per hidden layer.  Returns (masks + 'mlp_gates', stats) where the gate of every KEPT activation is
+    the implementation's, and stats bounds the disagreement with the oracle's own branch choice: how many kept
+    activations disagree, out of how many, and the largest |pre-activation| (relative to the layer's max) among them --
+    a disagreement is legitimate only right at the kink."""
+    B = x.shape[0]
+    pres = []
+    for lo in range(0, B, 32):
+        _, _, cache = orc.model_fwd(x[lo:lo + 32], params, cfg, _slice_masks(masks, lo, lo + 32))
+        pres.append(cache[4][4])
+    pres = [np.concatenate([c[i] for c in pres]) for i in range(len(pres[0]))]
+    out = dict(masks or {})
+    gates, n_dis, n_tot, worst = [], 0, 0, 0.0
+    for i, (z, g) in enumerate(zip(pres, gpu_gates)):
+        kept = (masks["mlp"][i] > 0) if masks and masks.get("mlp") is not None else np.ones_like(z, dtype=bool)
+        nat = z > 0
+        dis = kept & (nat != g)
+        n_dis += int(dis.sum()); n_tot += int(kept.sum())
+        if dis.any():
+            worst = max(worst, float(np.abs(z[dis]).max() / np.abs(z).max()))
+        gates.append(np.where(kept, g, nat))
+        # the aligned gates only move the branch of later layers' inputs by O(tol): later layers' natural gates are
+        # taken from the unaligned pass, which is what the implementation is compared against anyway
+    out["mlp_gates"] = gates
+    return out, {"disagree": n_dis, "kept": n_tot, "worst_rel_preact": worst}
