@@ -45,6 +45,11 @@ int mtadgat_conv_relu_bwd3(const float* x, const float* w, const float* y, const
                            const float* dy2, float* dx /*nullable*/, float* dw, float* db, int B, int n, int k, int ks,
                            void* stream);
 
+/* ConvLayer over B windows that start x_window_stride ELEMENTS apart: stride k = the overlapping slices of a
+ * device-resident (N,k) series (utils.py:107-120 SlidingWindowDataset.__getitem__, prediction.py:43-52), read in place. */
+int mtadgat_conv_relu_fwd_strided(const float* x, const float* w, const float* bias, float* y, int B, int n, int k, int ks,
+                                  long long x_window_stride, void* stream);
+
 /* ---- FeatureAttentionLayer.forward modules.py:65-95 (feature=1) / TemporalAttentionLayer.forward
  *      modules.py:166-193 (feature=0).  E = lin.weight.shape[0]; GATv2: lin_w (E,2D), a (E); GATv1: lin_w (E,D),
  *      a (2E); D = n (feature) or k (temporal); bias (K,K) nullable; out (B,n,k).
@@ -89,6 +94,11 @@ int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const float* w_hh
                         float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int B, int n, int Hs, int R,
                         int parts, void* stream);
 
+/* Scoring path: the same decoder emitting only its last state h_{n-1} (B,R) (prediction.py:62 keeps
+ * window_recon[:, -1, :] only).  scratch: mtadgat_gru_rep_saved_floats(B,n,Hs,R,0) floats. */
+int mtadgat_gru_rep_last(const float* h_src, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                         float* h_last, float* scratch, int B, int n, int Hs, int R, void* stream);
+
 /* ---- nn.Linear (+ReLU, +Dropout): Forecasting_Model.forward modules.py:307-311, recon fc modules.py:282.
  *      x (M,I), w (O,I), b (O), y (M,O); act 0 none / 1 relu. ---- */
 int mtadgat_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int I, int O, int act,
@@ -107,6 +117,14 @@ int mtadgat_rmse_pair_fwd(const float* preds, const float* y, long long n_pred, 
 int mtadgat_rmse_pair_bwd(const float* preds, const float* y, long long n_pred, const float* recons, const float* x,
                           long long n_rec, const float* losses, const float* g_forecast, const float* g_recon,
                           float* dpreds, float* drecons, void* stream);
+
+/* ---- anomaly-score epilogue of Predictor.get_score (prediction.py:65-91): a_score[i][c] = |preds[i][c] - actual| +
+ *      gamma |recons_last[i][c] - actual|, actual = series[n+i][target_dims ? target_dims[c] : c]; a_global[i] = mean_c
+ *      (nullable).  preds, recons_last, a_score are (n_windows, out); series (N,k) with N >= n + n_windows;
+ *      target_dims: `out` device ints or NULL. ---- */
+int mtadgat_score_epilogue(const float* preds, const float* recons_last, const float* series, const int* target_dims,
+                           int n, int k, int out, long long n_windows, float gamma, float* a_score,
+                           float* a_global /*nullable*/, void* stream);
 
 /* ---- recurrence implementation: 1 (default) = persistent tcgen05/TMEM kernel, fp16 operands with fp32
  *      accumulation and fp32 hidden state (hidden sizes 8..256); 0 = fp32 SIMT kernel.  mtadgat_tc_probe runs one

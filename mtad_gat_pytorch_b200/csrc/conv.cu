@@ -12,12 +12,14 @@ struct ConvShiftLoad {
   static constexpr bool fast_second = true;
   const float* src; const float* y; int n, k, pad, sgn;
   const float* src1; const float* src2;          // MASKED only: further gradient sources (nullable)
+  long long ws;                                  // elements between consecutive windows of src: n*k for a (B,n,k) batch,
+                                                 // k when the windows are the overlapping slices of a resident (N,k) series
   __device__ __forceinline__ float operator()(int, int m, int kk) const {
     int b = m / n, t = m - b * n;
     int tau = kk / k, c = kk - tau * k;
     int ts = t + sgn * (tau - pad);
     if (ts < 0 || ts >= n) return 0.f;
-    long long o = ((long long)b * n + ts) * k + c;
+    long long o = (long long)b * ws + (long long)ts * k + c;
     float v = __ldg(src + o);
     if (MASKED) {
       if (src1) v += __ldg(src1 + o);
@@ -107,7 +109,7 @@ template <bool MASKED> struct OpA<ConvShiftLoad<MASKED>> {
       int ts = c.t + f.sgn * (tau - f.pad);
       float val = 0.f;
       if (k0 + j < kend && ts >= 0 && ts < f.n) {
-        long long o = ((long long)c.b * f.n + ts) * f.k + ch;
+        long long o = (long long)c.b * f.ws + (long long)ts * f.k + ch;
         val = __ldg(f.src + o);
         if (MASKED) {
           if (f.src1) val += __ldg(f.src1 + o);
@@ -175,11 +177,28 @@ extern "C" int mtadgat_conv_relu_fwd(const float* x, const float* w, const float
   MG_CHECK_ARG(x && w && bias && y, "conv_relu_fwd: null pointer");
   MG_CHECK_ARG(B > 0 && n > 0 && k > 0 && ks > 0 && (ks & 1), "conv_relu_fwd: need B,n,k>0 and odd kernel_size (got %d)", ks);
   cudaStream_t s = (cudaStream_t)stream;
-  ConvShiftLoad<false> A{x, nullptr, n, k, (ks - 1) / 2, +1, nullptr, nullptr};
+  ConvShiftLoad<false> A{x, nullptr, n, k, (ks - 1) / 2, +1, nullptr, nullptr, (long long)n * k};
   ConvWFwd Bw{w, k, ks};
   StStrided C{y, 0, k, 1, bias, ACT_RELU, 0};
   launch_gemm_batched_precise(1, B * n, k, ks * k, A, Bw, C, s);      // feeds the ReLU gate (backward tests y > 0)
   MG_CHECK_LAUNCH("conv_relu_fwd");
+  return MTADGAT_OK;
+}
+
+// Same layer over B windows that start `x_window_stride` elements apart in x: with stride k the windows are the
+// overlapping length-n slices of a device-resident (N,k) series (utils.py:107-120 SlidingWindowDataset), read in place --
+// the (B,n,k) batch the reference's loader materialises on the host and copies over PCIe never exists.  y is (B,n,k).
+extern "C" int mtadgat_conv_relu_fwd_strided(const float* x, const float* w, const float* bias, float* y, int B, int n,
+                                             int k, int ks, long long x_window_stride, void* stream) {
+  MG_CHECK_ARG(x && w && bias && y, "conv_relu_fwd_strided: null pointer");
+  MG_CHECK_ARG(B > 0 && n > 0 && k > 0 && ks > 0 && (ks & 1) && x_window_stride > 0,
+               "conv_relu_fwd_strided: need B,n,k,stride>0 and odd kernel_size (got %d)", ks);
+  cudaStream_t s = (cudaStream_t)stream;
+  ConvShiftLoad<false> A{x, nullptr, n, k, (ks - 1) / 2, +1, nullptr, nullptr, x_window_stride};
+  ConvWFwd Bw{w, k, ks};
+  StStrided C{y, 0, k, 1, bias, ACT_RELU, 0};
+  launch_gemm_batched_precise(1, B * n, k, ks * k, A, Bw, C, s);
+  MG_CHECK_LAUNCH("conv_relu_fwd_strided");
   return MTADGAT_OK;
 }
 
@@ -192,7 +211,7 @@ extern "C" int mtadgat_conv_relu_bwd3(const float* x, const float* w, const floa
   const int pad = (ks - 1) / 2;
   if (dx) {
     // dx[b,t',ci] = sum_{tau,co} dpre[b, t'-tau+pad, co] * w[co,ci,tau]
-    ConvShiftLoad<true> A{dy, y, n, k, pad, -1, dy1, dy2};
+    ConvShiftLoad<true> A{dy, y, n, k, pad, -1, dy1, dy2, (long long)n * k};
     ConvWBwd Bw{w, k, ks};
     StStrided C{dx, 0, k, 1, nullptr, ACT_NONE, 0};
     launch_gemm_batched(1, B * n, k, ks * k, A, Bw, C, s);

@@ -717,6 +717,29 @@ extern "C" int mtadgat_gru_rep_fwd(const float* h_src, const float* w_ih, const 
   return MTADGAT_OK;
 }
 
+// Scoring path (prediction.py:59-63 keeps only window_recon[:, -1, :]): the decoder over the scrambled repeat, emitting
+// only its LAST state h_{n-1} (B,R) -- no (B,n,R) output, no saved gates.  scratch: mtadgat_gru_rep_saved_floats(B,n,Hs,R,0).
+extern "C" int mtadgat_gru_rep_last(const float* h_src, const float* w_ih, const float* w_hh, const float* b_ih,
+                                    const float* b_hh, float* h_last, float* scratch, int B, int n, int Hs, int R,
+                                    void* stream) {
+  MG_CHECK_ARG(h_src && w_ih && w_hh && b_ih && b_hh && h_last && scratch, "gru_rep_last: null pointer");
+  MG_CHECK_ARG(B > 0 && n > 0 && Hs > 0 && R > 0, "gru_rep_last: bad shape");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int G = 3 * R, J = rep_J(n, Hs);
+  float* wt = scratch; float* S = scratch + al4((size_t)3 * R * R);
+  {
+    const size_t sm = sizeof(float) * 32 * ((size_t)Hs + 1);
+    MG_CHECK_ARG(sm <= 200 * 1024, "gru_rep_last: source width %d too large", Hs);
+    if (sm > 48 * 1024) cudaFuncSetAttribute(rep_build_S_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    rep_build_S_kernel<<<cdiv(G, 32), 256, sm, s>>>(w_ih, n, Hs, G, J, S);
+  }
+  MG_COUNT_LAUNCH();
+  int rc = run_recurrence_fwd(nullptr, S, h_src, b_ih, J, Hs, w_hh, b_hh, wt, nullptr, h_last, nullptr, B, n, R, s);
+  if (rc) return rc;
+  MG_CHECK_LAUNCH("gru_rep_last");
+  return MTADGAT_OK;
+}
+
 extern "C" int mtadgat_gru_rep_bwd(const float* h_src, const float* w_ih, const float* w_hh, const float* out,
                                    const float* saved, const float* dout, float* scratch, float* dh_src,
                                    int dh_accumulate, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh, int B,

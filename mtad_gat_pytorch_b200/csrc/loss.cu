@@ -73,3 +73,46 @@ extern "C" int mtadgat_rmse_pair_bwd(const float* preds, const float* y, long lo
   MG_CHECK_LAUNCH("rmse_pair_bwd");
   return MTADGAT_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// anomaly-score epilogue of the scoring loop (prediction.py:65-91), fused: for window index i and output feature c
+//   actual = series[n + i][target(c)]
+//   a_score[i][c] = sqrt((preds - actual)^2) + gamma * sqrt((recons - actual)^2) = |preds - actual| + gamma |recons - actual|
+//   a_global[i]   = mean_c a_score[i][c]                                   (A_Score_Global when scale_scores is off)
+// The reference does this in numpy after copying every batch's preds/recons to the host.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) score_epilogue_kernel(const float* __restrict__ preds, const float* __restrict__ recons,
+                                                             const float* __restrict__ series, const int* __restrict__ target,
+                                                             int n, int k, int out, long long nw, float gamma,
+                                                             float* __restrict__ a_score, float* __restrict__ a_global) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long i = (long long)blockIdx.x * 8 + warp;           // one warp per window index
+  if (i >= nw) return;
+  float acc = 0.f;
+  for (int c = lane; c < out; c += 32) {
+    const int col = target ? target[c] : c;
+    const float actual = __ldg(series + (size_t)(n + i) * k + col);
+    const float p = __ldg(preds + (size_t)i * out + c), r = __ldg(recons + (size_t)i * out + c);
+    const float a = sqrtf((p - actual) * (p - actual)) + gamma * sqrtf((r - actual) * (r - actual));
+    a_score[(size_t)i * out + c] = a;
+    acc += a;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0 && a_global) a_global[i] = acc / (float)out;
+}
+}  // namespace
+
+extern "C" int mtadgat_score_epilogue(const float* preds, const float* recons_last, const float* series, const int* target_dims,
+                                      int n, int k, int out, long long n_windows, float gamma, float* a_score,
+                                      float* a_global, void* stream) {
+  MG_CHECK_ARG(preds && recons_last && series && a_score, "score_epilogue: null pointer");
+  MG_CHECK_ARG(n > 0 && k > 0 && out > 0 && out <= k && n_windows >= 0, "score_epilogue: bad shape");
+  if (n_windows == 0) return MTADGAT_OK;
+  score_epilogue_kernel<<<cdiv(n_windows, 8), 256, 0, (cudaStream_t)stream>>>(preds, recons_last, series, target_dims, n, k, out,
+                                                                           n_windows, gamma, a_score, a_global);
+  MG_COUNT_LAUNCH();
+  MG_CHECK_LAUNCH("score_epilogue");
+  return MTADGAT_OK;
+}

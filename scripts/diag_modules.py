@@ -5,9 +5,12 @@ import numpy as np, torch
 import mtad_gat_pytorch_b200 as mg
 
 torch.manual_seed(0)
-B, n, k, H = int(sys.argv[1]) if len(sys.argv) > 1 else 256, 100, 38, 150
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+k = int(sys.argv[3]) if len(sys.argv) > 3 else 38
+n = int(sys.argv[4]) if len(sys.argv) > 4 else 100
+H = 150
 PD = float(sys.argv[2]) if len(sys.argv) > 2 else 0.3
-model = mg.MTAD_GAT(38, 100, 38, forecast_n_layers=3, dropout=PD).cuda().train()
+model = mg.MTAD_GAT(k, n, k, forecast_n_layers=3, dropout=PD).cuda().train()
 with torch.no_grad():
     model.feature_gat.bias.normal_(); model.temporal_gat.bias.normal_()
 

@@ -121,3 +121,16 @@ def align_mlp_gates(gpu_gates, masks, x, params, cfg, tol=1e-3):
         # taken from the unaligned pass, which is what the implementation is compared against anyway
     out["mlp_gates"] = gates
     return out, {"disagree": n_dis, "kept": n_tot, "worst_rel_preact": worst}
+
+
+def align_conv_gates(gpu_xc, masks, x, params, cfg):
+    """Same bookkeeping for the ConvLayer's ReLU (orc.conv_fwd `gates`): gpu_xc = the implementation's conv output
+    (B,n,k).  Returns (masks + 'conv_gates', stats)."""
+    pre = orc.conv_fwd(x, params["conv.conv.weight"], params["conv.conv.bias"])[1][1]
+    g = np.asarray(gpu_xc) > 0
+    nat = pre > 0
+    dis = nat != g
+    out = dict(masks or {})
+    out["conv_gates"] = g
+    worst = float(np.abs(pre[dis]).max() / np.abs(pre).max()) if dis.any() else 0.0
+    return out, {"disagree": int(dis.sum()), "kept": int(pre.size), "worst_rel_preact": worst}

@@ -163,65 +163,64 @@ def rel_l2(a, b):
 
 @pytest.mark.parametrize("cfgname,k,n", [("c4", 512, 100), ("c5", 38, 512)])
 def test_large_shape_tc_backward(cfgname, k, n):
-    """BASELINE.json configs[3]/[4] shapes, backward in `tc` mode at batch 32, explicit output gradients (windows
-    independent).  (i) reconstruction path (dL/dpreds = 0, so the forecasting head's ReLU branches -- which the
-    fp16-operand recurrence can flip, see test_c2_batch256_... -- do not enter): dx of the first 2 windows == the
-    oracle's, and every parameter gradient == the fp32-mode kernels' (pinned to the oracle by
-    test_large_shape_backward_vs_oracle) to 1e-3 in max-norm AND in L2 (SURVEY 8d names both).  The GAT projection
-    gradients get 3e-3 in max-norm: these shapes evaluate 2e7 (C5) / 5e7 (C4) LeakyReLU slope decisions per window, and
-    two fp32-accurate evaluations still disagree on a handful of them; the L2 bound stays 1e-3.  (ii) full gradients:
-    split-batch additivity inside tc mode (same kernels, same branches: exact up to summation order)."""
+    """BASELINE.json configs[3]/[4] shapes, backward in `tc` mode (only fp32 mode was tested there).
+    (i) 3 windows against the oracle: preds, recons, dx and every parameter gradient to 1e-3 -- on the implementation's
+    ReLU branches (conv and forecasting head; see test_c2_batch256_...): at k=512 the conv pre-activation is a 3584-term
+    dot product and tensor-core fp32 accumulation leaves it within ~3e-5 of the oracle's, enough to move a few of the
+    150 000 conv gates; the disagreement is bounded (<= 2e-3 of the gates, all within 1e-3 of the kink).  The GAT
+    projection gradients get 3e-3: 1e7..5e7 LeakyReLU slope decisions per window, a handful of which differ between any
+    two fp32-accurate evaluations.  (ii) batch 32: split-batch additivity inside tc mode (same kernels, same branches)."""
     import mtad_gat_pytorch_b200 as mg
-    B = 32
     kwargs = dict(n_features=k, window_size=n, out_dim=k, forecast_n_layers=3, dropout=0.3)
     cfg = orc.Config(**kwargs)
     params = orc.make_params(cfg, seed=72, dtype=np.float32)
     m = build(kwargs, params)
     rng = np.random.default_rng(72)
+    B = 32
     x = torch.from_numpy(rng.random((B, n, k)).astype(np.float32)).cuda()
     gp = torch.from_numpy(rng.standard_normal((B, k)).astype(np.float32)).cuda()
     gr = torch.from_numpy(rng.standard_normal((B, n, k)).astype(np.float32)).cuda()
-    g0 = torch.zeros_like(gp)
 
-    def grads(xs, gps, grs):
+    def grads(xs, gps, grs, record=False):
         m.zero_grad(set_to_none=True)
         xs = xs.clone().requires_grad_(True)
+        rec = [] if record else None
+        m.forecasting_model._gate_record = rec
         p, r = m(xs)
+        m.forecasting_model._gate_record = None
         torch.autograd.backward([p, r], [gps, grs])
-        return {nm: q.grad.clone() for nm, q in m.named_parameters()}, xs.grad.clone(), p.detach(), r.detach()
+        return {nm: q.grad.clone() for nm, q in m.named_parameters()}, xs.grad.clone(), p.detach(), r.detach(), rec
 
     mg.set_mode("tc")
-    g_tc, dx_tc, p_tc, r_tc = grads(x, g0, gr)
-    mg.set_mode("fp32")
-    g_32, dx_32, p_32, r_32 = grads(x, g0, gr)
-    errs = {"preds": rel(p_tc, p_32.cpu().numpy()), "recons": rel(r_tc, r_32.cpu().numpy()),
-            "dx": rel(dx_tc, dx_32.cpu().numpy())}
-    l2 = {"dx": rel_l2(dx_tc, dx_32)}
-    for nm in g_tc:
-        if nm.startswith("forecasting_model."):
-            assert float(g_tc[nm].abs().max()) == 0.0
-            continue
-        errs["grad." + nm] = rel(g_tc[nm], g_32[nm].cpu().numpy())
-        l2["grad." + nm] = rel_l2(g_tc[nm], g_32[nm])
-    xs = x[:2].cpu().numpy()
-    _, _, cache = orc.model_fwd(xs, params, cfg)
-    dx_ref, _ = orc.model_bwd(np.zeros((2, k), np.float32), gr[:2].cpu().numpy(), cache, params, cfg)
-    errs["dx.oracle"] = rel(dx_tc[:2], dx_ref)
-    # (ii) additivity with the full gradients
-    mg.set_mode("tc")
-    gf, dxf, _, _ = grads(x, gp, gr)
-    ga, dxa, _, _ = grads(x[:16].contiguous(), gp[:16].contiguous(), gr[:16].contiguous())
-    gb, dxb, _, _ = grads(x[16:].contiguous(), gp[16:].contiguous(), gr[16:].contiguous())
+    nb = 3
+    g3, dx3, p3, r3, rec = grads(x[:nb].contiguous(), gp[:nb].contiguous(), gr[:nb].contiguous(), record=True)
+    with torch.no_grad():
+        xc = m.conv(x[:nb].contiguous())
+    xs = x[:nb].cpu().numpy()
+    masks, st_c = ot.align_conv_gates(xc.cpu().numpy(), None, xs, params, cfg)
+    masks, st_m = ot.align_mlp_gates([g_.cpu().numpy() for g_ in rec], masks, xs, params, cfg)
+    print(f"[{cfgname} tc] ReLU branch disagreements: conv {st_c} mlp {st_m}")
+    assert st_c["disagree"] <= 2e-3 * st_c["kept"] and st_c["worst_rel_preact"] < 1e-3, st_c
+    assert st_m["disagree"] <= 5e-3 * st_m["kept"] and st_m["worst_rel_preact"] < 2e-3, st_m
+    p_ref, r_ref, cache = orc.model_fwd(xs, params, cfg, masks)
+    dx_ref, g_ref = orc.model_bwd(gp[:nb].cpu().numpy(), gr[:nb].cpu().numpy(), cache, params, cfg)
+    errs = {"preds": rel(p3, p_ref), "recons": rel(r3, r_ref), "dx": rel(dx3, dx_ref)}
+    for nm in g3:
+        errs["grad." + nm] = rel(g3[nm], g_ref[nm])
+    # (ii) additivity at batch 32
+    gf, dxf, _, _, _ = grads(x, gp, gr)
+    ga, dxa, _, _, _ = grads(x[:16].contiguous(), gp[:16].contiguous(), gr[:16].contiguous())
+    gb, dxb, _, _, _ = grads(x[16:].contiguous(), gp[16:].contiguous(), gr[16:].contiguous())
     for nm in gf:
         errs["add." + nm] = rel(ga[nm] + gb[nm], gf[nm].cpu().numpy())
     errs["add.dx"] = rel(torch.cat([dxa, dxb]), dxf.cpu().numpy())
-    worst, worst2 = max(errs, key=errs.get), max(l2, key=l2.get)
-    print(f"[{cfgname} tc bwd B=32] worst max-norm {worst} = {errs[worst]:.3e}; worst L2 {worst2} = {l2[worst2]:.3e}")
+    worst = max(errs, key=errs.get)
+    print(f"[{cfgname} tc bwd] worst {worst} = {errs[worst]:.3e}; " +
+          " ".join(f"{k_}={v:.1e}" for k_, v in sorted(errs.items(), key=lambda kv: -kv[1])[:6]))
 
     def tol(name):
         return 3e-3 if ("_gat.lin." in name and name.startswith("grad.")) else TOL
     bad = {k_: e for k_, e in errs.items() if not e < tol(k_)}
-    bad.update({"l2." + k_: e for k_, e in l2.items() if not e < TOL})
     assert not bad, bad
 
 

@@ -1,6 +1,6 @@
 """2-rank NCCL test of the REAL model (DDP correctness was only tested on a toy net over gloo): windows
-shard over the batch, the backward kernels write into the flat GradBucket, the early/late all-reduces average it in
-place, and the result equals the mean of the per-shard oracle gradients; the one-graph step (collectives captured)
+shard over the batch, the backward kernels write into the flat GradBucket, one all-reduce averages it in place, and the
+result equals the mean of the per-shard oracle gradients; the graph step (fwd/bwd graph, eager collective, Adam graph)
 keeps the replicas bit-identical and agrees with the eager step.  Needs 2 GPUs (gpurun --gpus 2); skipped otherwise."""
 import os
 
@@ -39,7 +39,9 @@ def _worker(rank, world, port, ret):
         return m.to(dev).train()
 
     out = {}
-    # (1) eager: gradients after the bucket all-reduce == mean over ranks of the per-shard oracle gradients
+    # (1) eager: gradients after the bucket all-reduce == mean over ranks of the per-shard oracle gradients (fp32 kernels:
+    #     this checks the data-parallel plumbing, not the tensor-core arithmetic)
+    mg.set_mode("fp32")
     m = fresh()
     opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True, fused=True)
     step = mgt.TrainStep(m, opt, batch=hi - lo, use_graph=False, world_size=world)
@@ -57,10 +59,13 @@ def _worker(rank, world, port, ret):
         ref = g_mean[name] / world
         errs[name] = float(np.abs(p.grad.cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1e-9))
     out["grad_err"] = max(errs.values())
-    # (2) three optimisation steps: one-graph step (collectives captured) vs eager step
+    mg.set_mode("tc")
+    # (2) three optimisation steps: graph step vs eager step
     finals = {}
-    for tag, kw in (("graph", dict(use_graph=True)), ("eager", dict(use_graph=False)),
-                    ("graph_nooverlap", dict(use_graph=True, overlap_comm=False))):
+    variants = [("graph", dict(use_graph=True)), ("eager", dict(use_graph=False))]
+    if os.environ.get("MTADGAT_TEST_CAPTURED_COMM"):       # opt-in: collectives captured into the step graph
+        variants.append(("graph_captured", dict(use_graph=True, capture_comm=True)))
+    for tag, kw in variants:
         m = fresh()
         opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True, fused=True)
         step = mgt.TrainStep(m, opt, batch=hi - lo, world_size=world, **kw)
@@ -73,13 +78,16 @@ def _worker(rank, world, port, ret):
         out[tag + "_replicas_equal"] = all(torch.equal(o, others[0]) for o in others)
         finals[tag] = flat
         if tag == "graph":
-            out["one_graph"] = step.g_opt is None and step.g_fb is not None
+            out["two_graphs"] = step.g_opt is not None and step.g_fb is not None
+        step.release()
     upd = float((finals["eager"] - torch.cat([torch.from_numpy(params[k].astype(np.float32)).reshape(-1)
                                                for k, _ in m.named_parameters()]).to(dev)).norm())
     out["graph_vs_eager"] = float((finals["graph"] - finals["eager"]).norm()) / upd
-    out["nooverlap_vs_eager"] = float((finals["graph_nooverlap"] - finals["eager"]).norm()) / upd
+    if "graph_captured" in finals:
+        out["captured_vs_eager"] = float((finals["graph_captured"] - finals["eager"]).norm()) / upd
     ret[rank] = out
-    dist.destroy_process_group()
+    torch.cuda.synchronize()
+    os._exit(0)            # results are with the parent; skip communicator teardown (it can block on exit ordering)
 
 
 def test_two_rank_nccl_model_gradients_and_one_graph_step():
@@ -88,12 +96,19 @@ def test_two_rank_nccl_model_gradients_and_one_graph_step():
     mgr = mp.Manager()
     ret = mgr.dict()
     port = 29500 + os.getpid() % 400
-    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    ctx = mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=False)
+    import time
+    t0 = time.time()
+    while not ctx.join(timeout=5):
+        if time.time() - t0 > 240:
+            for p in ctx.processes:
+                p.kill()
+            pytest.fail(f"workers did not finish in 240 s; partial results {dict(ret)}")
     assert len(ret) == 2
     for rank, out in ret.items():
         print(f"[nccl rank {rank}] {out}")
         assert out["adopted"], "gradient views were not adopted by autograd: the bucket path is not in use"
         assert out["grad_err"] < 1e-3, out
-        assert out["one_graph"]
-        assert out["graph_replicas_equal"] and out["eager_replicas_equal"] and out["graph_nooverlap_replicas_equal"]
-        assert out["graph_vs_eager"] < 0.05 and out["nooverlap_vs_eager"] < 0.05, out
+        assert out["two_graphs"]
+        assert out["graph_replicas_equal"] and out["eager_replicas_equal"]
+        assert out["graph_vs_eager"] < 0.05 and out.get("captured_vs_eager", 0.0) < 0.05, out
