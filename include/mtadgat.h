@@ -60,6 +60,11 @@ long long mtadgat_gat_bwd_scratch_floats(int B, int n, int k, int E, int feature
 int mtadgat_gat_fwd(const float* x, const float* lin_w, const float* lin_b, const float* a, const float* bias,
                     float* out, float* saved, int B, int n, int k, int E, int feature, int use_gatv2, float alpha,
                     int save_att, float p_drop, const unsigned long long* seed, void* stream);
+/* GAT forward structure for layers whose window fits one CTA (K <= 128 nodes): 1 (default) = ONE fused kernel per layer
+ * (in-kernel tcgen05 projection of the window from packed weights, P/Q kept in shared memory, score, softmax, dropout,
+ * aggregation, sigmoid); 0 = projection GEMM to HBM + score kernel.  Results are identical. */
+int mtadgat_set_gat_impl(int impl);
+int mtadgat_get_gat_impl(void);
 int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* lin_b, const float* a, const float* out,
                     const float* gout, const float* saved, float* scratch, float* dx, int dx_accumulate,
                     float* dlin_w, float* dlin_b, float* da, float* dbias /*nullable*/, int B, int n, int k, int E,

@@ -442,6 +442,12 @@ def set_gemm_impl(name):
     check(lib.mtadgat_set_gemm_impl({"fp32": 0, "tc": 1, "tc_gather": 2}[name]))
 
 
+def set_gat_impl(name):
+    """'fused' (default): one kernel per GAT layer forward (in-kernel tcgen05 projection + score + softmax + aggregation);
+    'split': projection GEMM to HBM followed by the score kernel."""
+    check(lib.mtadgat_set_gat_impl({"split": 0, "fused": 1}[name]))
+
+
 def set_mode(name):
     """'tc': tensor cores everywhere (default); 'fp32': every kernel on the fp32 SIMT path."""
     set_gemm_impl("fp32" if name == "fp32" else "tc")

@@ -477,9 +477,11 @@ def test_pack_workspace_cannot_grow_during_capture():
     inside a capture fails loudly (nothing launched, message names mtadgat_workspace_reserve); after an eager call on
     the same stream the capture succeeds."""
     import mtad_gat_pytorch_b200 as mg
-    from mtad_gat_pytorch_b200._lib import MtadGatLibraryError
+    from mtad_gat_pytorch_b200._lib import MtadGatLibraryError, lib
     lin = mg.Forecasting_Model(64, 64, 64, 1, 0.0).cuda().eval()
     x = torch.rand(300, 64, device="cuda")
+    torch.cuda.synchronize()
+    lib.mtadgat_workspace_release()        # torch hands out pooled streams: an earlier test may have grown this one's buffer
     s = torch.cuda.Stream()
     g = torch.cuda.CUDAGraph()
     with pytest.raises(MtadGatLibraryError, match="workspace"):
@@ -516,3 +518,44 @@ def test_pack_workspace_growth_keeps_captured_graphs_valid():
     out.zero_()
     g.replay(); torch.cuda.synchronize()
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("shape", [(38, 100, True), (38, 100, False), (55, 100, True), (25, 100, True), (6, 20, True), (6, 20, False)])
+def test_fused_gat_kernel_equals_projection_gemm_plus_score_kernel(shape):
+    """The fused layer kernel (in-kernel tcgen05 projection from packed three-term weights, P/Q kept in shared memory)
+    computes what the two-kernel path computes (projection GEMM to HBM, then the score kernel): same outputs in eval and
+    train mode (same Philox masks), and -- through the P/Q it writes out in training -- the same gradients."""
+    import mtad_gat_pytorch_b200 as mg
+    k, n, v2 = shape
+    torch.manual_seed(11)
+    B = 37
+    x = torch.rand(B, n, k, device="cuda")
+    go = torch.randn(B, n, k, device="cuda")
+    for cls in (mg.FeatureAttentionLayer, mg.TemporalAttentionLayer):
+        layer = cls(k, n, 0.3, 0.2, None, v2).cuda()
+        with torch.no_grad():
+            layer.bias.normal_()
+        res = {}
+        try:
+            for impl in ("split", "fused"):
+                mg.set_gat_impl(impl)
+                layer.eval()
+                with torch.no_grad():
+                    y_eval = layer(x)
+                layer.train()
+                mg.manual_seed(5)
+                layer.zero_grad(set_to_none=True)
+                xi = x.clone().requires_grad_(True)
+                y = layer(xi)
+                y.backward(go)
+                torch.cuda.synchronize()
+                res[impl] = (y_eval, y.detach(), xi.grad.clone(), [p.grad.clone() for p in layer.parameters()])
+        finally:
+            mg.set_gat_impl("fused")
+        a, b_ = res["split"], res["fused"]
+        gmax = max(float(v.abs().max()) for v in a[3])       # a gradient that is identically zero in exact arithmetic (v1
+        errs = [rel(b_[0], a[0].cpu().numpy()), rel(b_[1], a[1].cpu().numpy()), rel(b_[2], a[2].cpu().numpy())] + \
+               [float((u - v).abs().max()) / max(float(v.abs().max()), 1e-4 * gmax)      # feature lin.bias) is pure rounding noise
+                for u, v in zip(b_[3], a[3])]
+        print(f"[fused vs split {cls.__name__} k={k} n={n} v2={v2}] " + " ".join(f"{e:.1e}" for e in errs))
+        assert max(errs) < 1e-4, errs          # tiny shapes: gradients near the 1e-6 floor of rel()
