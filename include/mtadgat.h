@@ -166,6 +166,32 @@ void mtadgat_gru_debug_buffer(long long* dev_ptr);   /* optional: 16 int64 per-p
 int mtadgat_tc_mma_bench(int ntiles, int kchunks, int M, int N, int iters, int row_stride, int nissuers, int mode,
                          long long* out_cycles, void* stream);
 
+/* ---- CPU backend (host pointers, synchronous, fp32, OpenMP over windows): the same stages for tensors that live on the
+ *      host -- the reference's callers pick the device from the tensors (training.py:60, prediction.py:45) and
+ *      BASELINE.json's first configuration is a CPU forward.  Selected by the tensors' device; CUDA tensors never come
+ *      here.  att (B,K,K): softmax output, written when non-null and required by the backward; gates (B,n,4H) likewise.
+ *      Dropout uses the same Philox streams as the CUDA kernels, seeded by value. ---- */
+int mtadgat_cpu_conv_relu_fwd(const float* x, const float* w, const float* bias, float* y, int B, int n, int k, int ks);
+int mtadgat_cpu_conv_relu_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx /*nullable*/,
+                              float* dw, float* db, int B, int n, int k, int ks);
+int mtadgat_cpu_gat_fwd(const float* x, const float* lin_w, const float* lin_b, const float* a, const float* bias,
+                        float* out, float* att /*nullable*/, int B, int n, int k, int E, int feature, int use_gatv2,
+                        float alpha, float p_drop, unsigned long long seed);
+int mtadgat_cpu_gat_bwd(const float* x, const float* lin_w, const float* lin_b, const float* a, const float* att,
+                        const float* out, const float* gout, float* dx, float* dlin_w, float* dlin_b, float* da,
+                        float* dbias /*nullable*/, int B, int n, int k, int E, int feature, int use_gatv2, float alpha,
+                        float p_drop, unsigned long long seed);
+int mtadgat_cpu_gru_fwd(const float* x, const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh,
+                        float* out, float* gates /*nullable*/, int B, int n, int I, int H);
+int mtadgat_cpu_gru_bwd(const float* x, const float* w_ih, const float* w_hh, const float* out, const float* gates,
+                        const float* dout, float* dx /*nullable*/, float* dw_ih, float* dw_hh, float* db_ih, float* db_hh,
+                        int B, int n, int I, int H);
+int mtadgat_cpu_linear_fwd(const float* x, const float* w, const float* b, float* y, int M, int I, int O, int act,
+                           float p_drop, unsigned long long seed, unsigned int rng_stream);
+int mtadgat_cpu_linear_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx /*nullable*/,
+                           float* dw, float* db, int M, int I, int O, int act, float p_drop, unsigned long long seed,
+                           unsigned int rng_stream);
+
 /* ---- RNG plumbing ---- */
 int mtadgat_dropout_mask(float* out, long long numel, float p, const unsigned long long* seed,
                          unsigned int rng_stream, void* stream);   /* multipliers 0 or 1/(1-p), for tests */

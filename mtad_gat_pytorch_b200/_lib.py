@@ -14,6 +14,7 @@ _I = ctypes.c_int
 _F = ctypes.c_float
 _U = ctypes.c_uint
 _LL = ctypes.c_longlong
+_ULL = ctypes.c_ulonglong
 
 # name -> (restype, argtypes); mirrors include/mtadgat.h one to one
 SIGNATURES = {
@@ -60,6 +61,14 @@ SIGNATURES = {
     "mtadgat_tc_probe": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mtadgat_gru_debug_buffer": (None, [_P]),
     "mtadgat_tc_mma_bench": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "mtadgat_cpu_conv_relu_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I]),
+    "mtadgat_cpu_conv_relu_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
+    "mtadgat_cpu_gat_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _ULL]),
+    "mtadgat_cpu_gat_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _F, _ULL]),
+    "mtadgat_cpu_gru_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
+    "mtadgat_cpu_gru_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I]),
+    "mtadgat_cpu_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _ULL, _U]),
+    "mtadgat_cpu_linear_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _ULL, _U]),
     "mtadgat_dropout_mask": (_I, [_P, _LL, _F, _P, _U, _P]),
     "mtadgat_seed_advance": (_I, [_P, _P]),
 }

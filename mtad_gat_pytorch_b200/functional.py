@@ -64,7 +64,11 @@ _seed_state = {}
 
 
 def fresh_seed(device):
-    """Advance the per-device seed and return a private copy (kept by autograd for the backward)."""
+    """Advance the per-device seed and return a private copy (kept by autograd for the backward).  Host tensors: the
+    CPU backend's seed, returned by value."""
+    if torch.device(device).type == "cpu":
+        from . import cpu_backend
+        return cpu_backend.fresh_seed()
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     st = _seed_state.get(key)
     if st is None:
@@ -74,9 +78,27 @@ def fresh_seed(device):
     return st.clone()
 
 
+def dropout_multipliers_cpu(numel, p, seed, rng_stream):
+    """Host-side multipliers of (seed, stream): the CPU backend's linear layer with zero weights and unit bias applies
+    exactly the mask (used for nn.GRU's inter-layer dropout on host tensors)."""
+    from . import cpu_backend
+    x = torch.zeros(int(numel), 1)
+    w = torch.zeros(1, 1)
+    b = torch.ones(1)
+    return cpu_backend.LinearFn.apply(x, w, b, 0, float(p), int(seed), int(rng_stream)).reshape(-1)
+
+
 def manual_seed(seed, device=None):
     """Re-seed the dropout stream of `device`.  The state tensor is updated IN PLACE: a CUDA graph captured earlier
     holds its address (seed_advance_kernel), so replays after a re-seed draw from the new seed."""
+    from . import cpu_backend
+    if device is None:
+        cpu_backend.manual_seed(seed)                    # no device given: re-seed the host stream too
+        if not torch.cuda.is_available():
+            return
+    elif torch.device(device).type == "cpu":
+        cpu_backend.manual_seed(seed)
+        return
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
     st = _seed_state.get(key)

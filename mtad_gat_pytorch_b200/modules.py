@@ -1,5 +1,8 @@
 """Host-side mirror of the reference's `modules.py` classes for the B200 hot path.
 
+Device dispatch: CUDA tensors run the sm_100a kernels (functional.py); host tensors run the library's own CPU backend
+(cpu_backend.py -> `mtadgat_cpu_*`), as the reference's callers expect (training.py:60).  Never one for the other.
+
 Same class names, constructor signatures, parameter names/shapes (hence the same state-dict and, because the
 parameter containers are constructed in the same order with the same torch initialisers, the same values
 under the same torch seed) and forward signatures as the reference.  The `nn.Conv1d`,
@@ -10,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F
+from . import cpu_backend as C
 
 
 class _SeedMixin:
@@ -33,6 +37,8 @@ class ConvLayer(nn.Module):
         self.conv = nn.Conv1d(in_channels=n_features, out_channels=n_features, kernel_size=kernel_size)
 
     def forward(self, x):
+        if not x.is_cuda:
+            return C.ConvReluFn.apply(x, self.conv.weight, self.conv.bias)
         return F.ConvReluFn.apply(x, self.conv.weight, self.conv.bias)
 
     def forward_fanout(self, x, fanout):
@@ -69,6 +75,9 @@ class _GraphAttention(nn.Module, _SeedMixin):
 
     def forward(self, x):
         p = self.dropout if self.training else 0.0
+        if not x.is_cuda:
+            return C.GatFn.apply(x, self.lin.weight, self.lin.bias, self.a, self.bias if self.use_bias else None,
+                                 self._feature, self.use_gatv2, self.alpha, p, self._seed(x.device, p))
         return F.GatFn.apply(x, self.lin.weight, self.lin.bias, self.a, self.bias if self.use_bias else None,
                              self._feature, self.use_gatv2, self.alpha, p, self._seed(x.device, p))
 
@@ -109,6 +118,11 @@ class GRULayer(nn.Module, _SeedMixin):
 
     def _run(self, slices, need_out):
         g = self.gru
+        if not slices[0].is_cuda:
+            x = slices[0] if len(slices) == 1 else torch.cat(list(slices), dim=2)      # mtad_gat.py:71
+            out = C.gru_layers(g, x, self.n_layers, self.dropout, self.training,
+                               lambda: self._step_seed if self._step_seed is not None else F.fresh_seed(x.device), F.RNG_GRU0)
+            return out, out[:, -1, :]
         xs = list(slices) + [None] * (3 - len(slices))
         multi = self.n_layers > 1
         layer0 = F.GruFn.apply(xs[0], xs[1], xs[2], g.weight_ih_l0, g.weight_hh_l0, g.bias_ih_l0, g.bias_hh_l0,
@@ -148,11 +162,17 @@ class RNNDecoder(nn.Module, _SeedMixin):
     def forward_repeat(self, h_end, window_size):
         """Decoder over the reference's scrambled repeat of h_end (modules.py:279) without building it."""
         r = self.rnn
+        if not h_end.is_cuda:
+            rep = h_end.repeat_interleave(int(window_size), dim=1).view(h_end.size(0), int(window_size), -1)   # modules.py:279
+            return self.forward(rep)
         out = F.GruRepFn.apply(h_end, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, int(window_size))
         return self._finish(out, h_end.device)
 
     def forward(self, x):
         r = self.rnn
+        if not x.is_cuda:
+            return C.gru_layers(r, x, self.n_layers, self.dropout, self.training,
+                                lambda: self._step_seed if self._step_seed is not None else F.fresh_seed(x.device), F.RNG_DEC0)
         out, _ = F.GruFn.apply(x, None, None, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0, True)
         return self._finish(out, x.device)
 
@@ -168,6 +188,8 @@ class ReconstructionModel(nn.Module):
 
     def forward(self, x):
         dec = self.decoder.forward_repeat(x, self.window_size)
+        if not x.is_cuda:
+            return C.LinearFn.apply(dec, self.fc.weight, self.fc.bias, 0, 0.0, None, 0)
         return F.LinearFn.apply(dec, self.fc.weight, self.fc.bias, 0, 0.0, None, 0)
 
 
@@ -187,8 +209,9 @@ class Forecasting_Model(nn.Module, _SeedMixin):
         p = self.dropout.p if self.training else 0.0
         seed = self._seed(x.device, p)
         rec = getattr(self, "_gate_record", None)       # tests: a list collects (activation > 0) per hidden layer
+        Lin = F.LinearFn if x.is_cuda else C.LinearFn
         for i in range(len(self.layers) - 1):
-            x = F.LinearFn.apply(x, self.layers[i].weight, self.layers[i].bias, 1, p, seed, F.RNG_MLP0 + i)
+            x = Lin.apply(x, self.layers[i].weight, self.layers[i].bias, 1, p, seed, F.RNG_MLP0 + i)
             if rec is not None:
                 rec.append(x.detach() > 0)
-        return F.LinearFn.apply(x, self.layers[-1].weight, self.layers[-1].bias, 0, 0.0, None, 0)
+        return Lin.apply(x, self.layers[-1].weight, self.layers[-1].bias, 0, 0.0, None, 0)

@@ -9,7 +9,8 @@ from .modules import (ConvLayer, FeatureAttentionLayer, TemporalAttentionLayer, 
 
 
 class MTAD_GAT(nn.Module):
-    """x (B, n, k) float32 CUDA  ->  (predictions (B, out_dim), recons (B, n, out_dim)).
+    """x (B, n, k) float32  ->  (predictions (B, out_dim), recons (B, n, out_dim)).  CUDA tensors run the sm_100a kernels,
+    host tensors the library's CPU backend (the device is the tensors', as in the reference).
 
     Arguments are the reference's (mtad_gat.py:37-54), positionally compatible with train.py:74-90."""
 
@@ -44,11 +45,17 @@ class MTAD_GAT(nn.Module):
         return (self.feature_gat, self.temporal_gat, self.gru, self.forecasting_model, self.recon_model.decoder)
 
     def forward(self, x):
-        F.require_cuda(x, "MTAD_GAT input")
         seed = F.fresh_seed(x.device) if (self.training and self._dropout > 0.0) else None
         for m in self._seeded():
             m._step_seed = seed
         try:
+            if not x.is_cuda:
+                # host tensors: the library's CPU backend, stage by stage (no streams to fork)
+                xc = self.conv(x)
+                h_feat = self.feature_gat(xc)
+                h_temp = self.temporal_gat(xc)
+                h_end = self.gru.forward_slices([xc, h_feat, h_temp])
+                return self.forecasting_model(h_end), self.recon_model(h_end)
             # mtad_gat.py:67 -- one result, three handles (GRU slice, feature GAT, temporal GAT): see ConvReluFn
             xc, xc_f, xc_t = self.conv.forward_fanout(x, 3)
             if self.branch_parallel:

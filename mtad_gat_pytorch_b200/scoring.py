@@ -10,8 +10,8 @@ Here the (N,k) series lives in HBM once.  Window j is the slice series[j : j+n],
 sample i+1 (cat(x_i[1:], y_i) == x_{i+1}), so each distinct window is run ONCE: window j yields preds_j (the forecast of
 row j+n) and the last reconstructed row of window j (the decoder emits only its last state,
 `mtadgat_gru_rep_last`).  Forecast_i = preds(x_i), Recon_i = recon_last(x_{i+1}), i = 0 .. N-n-1, and the score epilogue
-runs on the device (`mtadgat_score_epilogue`).  Results equal the reference's double forward (tests: the oracle's
-`score_batch` and the shipped SMD-1-1 Forecast_/Recon_ columns).
+runs on the device (`mtadgat_score_epilogue`).  Results equal the reference's double forward (tests/test_gpu_scoring.py: the CPU
+restatement of prediction.py:55-63 and the shipped SMD-1-1 Forecast_/Recon_ columns).
 """
 import numpy as np
 import torch

@@ -1,5 +1,5 @@
 """CPU tests: the C-ABI library builds, loads without a GPU and exports every symbol include/mtadgat.h
-declares; host-side logic (state-dict contract, shape queries, no-CPU-fallback rule)."""
+declares; host-side logic (state-dict contract, shape queries, dispatch by tensor device)."""
 import ctypes
 import os
 import re
@@ -74,12 +74,17 @@ def test_constructor_signature_matches_reference_call_site(mg):
         mg.ConvLayer(5, 4)                             # even kernel sizes change the window length
 
 
-def test_no_cpu_fallback(mg):
-    m = mg.MTAD_GAT(5, 12, 5)
+def test_device_dispatch_is_by_tensor_device_only(mg):
+    """Host tensors run the library's CPU backend (returning host tensors); the CUDA bridges refuse host tensors, so a
+    CUDA model can never silently compute on the CPU."""
+    from mtad_gat_pytorch_b200 import functional as F
+    m = mg.MTAD_GAT(5, 12, 5).eval()
+    with torch.no_grad():
+        p, r = m(torch.rand(2, 12, 5))
+    assert p.shape == (2, 5) and r.shape == (2, 12, 5) and p.device.type == "cpu"
+    w, b = m.conv.conv.weight, m.conv.conv.bias
     with pytest.raises(mg.MtadGatLibraryError):
-        m(torch.rand(2, 12, 5))
-    with pytest.raises(mg.MtadGatLibraryError):
-        m.conv(torch.rand(2, 12, 5))
+        F.ConvReluFn.apply(torch.rand(2, 12, 5), w, b)             # the CUDA bridge itself never accepts host tensors
 
 
 def test_product_never_imports_oracle():

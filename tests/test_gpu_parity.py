@@ -285,11 +285,25 @@ def test_dropout_masks_and_train_mode_parity():
     assert not torch.equal(preds, preds2)
 
 
-def test_cpu_tensor_raises_no_fallback():
+def test_cuda_tensors_never_take_the_cpu_backend():
+    """Dispatch is by tensor device: a CUDA forward launches this library's kernels (launch counter moves, outputs on the
+    GPU) and agrees with the same model run on host tensors by the CPU backend; the CUDA bridges reject host tensors."""
     import mtad_gat_pytorch_b200 as mg
-    m = mg.MTAD_GAT(5, 12, 5)
+    from mtad_gat_pytorch_b200 import functional as F
+    torch.manual_seed(3)
+    m = mg.MTAD_GAT(5, 12, 5).eval()
+    x = torch.rand(2, 12, 5)
+    with torch.no_grad():
+        p_cpu, r_cpu = m(x)
+    assert p_cpu.device.type == "cpu"
+    m.cuda()
+    mg.reset_launch_count()
+    with torch.no_grad():
+        p_gpu, r_gpu = m(x.cuda())
+    assert p_gpu.is_cuda and mg.launch_count() >= 10
+    assert rel(p_gpu, p_cpu.numpy()) < TOL and rel(r_gpu, r_cpu.numpy()) < TOL
     with pytest.raises(mg.MtadGatLibraryError):
-        m(torch.rand(2, 12, 5))
+        F.ConvReluFn.apply(x, m.conv.conv.weight, m.conv.conv.bias)
 
 
 def _full_size_model(k, n, out_dim, seed):
