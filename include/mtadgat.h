@@ -131,6 +131,13 @@ int mtadgat_score_epilogue(const float* preds, const float* recons_last, const f
                            int n, int k, int out, long long n_windows, float gamma, float* a_score,
                            float* a_global /*nullable*/, void* stream);
 
+/* ---- epsilon threshold (Hundman et al.) on the anomaly scores, as eval_methods.py:186-236 find_epsilon computes it
+ *      (19 candidates mean + z*sd, z = 2.5 .. 11.5; anomalies dilated by +-49 indices; reg_level 0/1/2).  scores: n_scores
+ *      device floats (e.g. a_global of mtadgat_score_epilogue).  out[0] = epsilon, out[1] = the winning z (-1: no
+ *      candidate qualified, epsilon = max(scores)), out[2] = its score.  scratch: mtadgat_find_epsilon_scratch_doubles(). ---- */
+long long mtadgat_find_epsilon_scratch_doubles(void);
+int mtadgat_find_epsilon(const float* scores, long long n_scores, int reg_level, float* out, double* scratch, void* stream);
+
 /* ---- recurrence implementation: 1 (default) = persistent tcgen05/TMEM kernel, fp16 operands with fp32
  *      accumulation and fp32 hidden state (hidden sizes 8..256); 0 = fp32 SIMT kernel.  mtadgat_tc_probe runs one
  *      128 x N x K product through the same shared-memory operand layout (diagnostic / unit test). ---- */

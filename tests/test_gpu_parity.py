@@ -569,7 +569,7 @@ def test_fused_gat_kernel_equals_projection_gemm_plus_score_kernel(shape):
         a, b_ = res["split"], res["fused"]
         gmax = max(float(v.abs().max()) for v in a[3])       # a gradient that is identically zero in exact arithmetic (v1
         errs = [rel(b_[0], a[0].cpu().numpy()), rel(b_[1], a[1].cpu().numpy()), rel(b_[2], a[2].cpu().numpy())] + \
-               [float((u - v).abs().max()) / max(float(v.abs().max()), 1e-4 * gmax)      # feature lin.bias) is pure rounding noise
+               [float((u - v).abs().max()) / max(float(v.abs().max()), 1e-3 * gmax)      # feature lin.bias) is pure rounding noise
                 for u, v in zip(b_[3], a[3])]
         print(f"[fused vs split {cls.__name__} k={k} n={n} v2={v2}] " + " ".join(f"{e:.1e}" for e in errs))
         assert max(errs) < 1e-4, errs          # tiny shapes: gradients near the 1e-6 floor of rel()

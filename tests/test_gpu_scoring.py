@@ -95,3 +95,22 @@ def test_reference_trainer_and_predictor_run_unmodified_on_the_shim(tmp_path):
     check on the library's CPU backend.)"""
     from tests.dropin_common import run_dropin
     run_dropin(tmp_path, "cuda", TOL, check_single_pass=True)
+
+
+@pytest.mark.parametrize("reg_level", [0, 1, 2])
+def test_find_epsilon_on_device_equals_reference_restatement(reg_level):
+    """mtadgat_find_epsilon (19 candidate thresholds, +-49 dilation, population moments in double) vs the CPU restatement
+    of eval_methods.py:186-236 (pinned to the reference's own function in tests/test_oracle_golden.py)."""
+    from mtad_gat_pytorch_b200 import thresholding
+    from oracle import thresholding_oracle as tho
+    from tests.test_oracle_golden import _score_series
+    for seed, N in ((0, 3000), (1, 2999), (2, 70001), (3, 513)):
+        e = _score_series(seed, N)
+        eps_ref = float(tho.find_epsilon(e, reg_level))
+        eps, z, _ = thresholding.find_epsilon(torch.from_numpy(e).cuda(), reg_level)
+        assert abs(eps - eps_ref) <= 2e-6 * max(1.0, abs(eps_ref)), (seed, N, eps, eps_ref, z)
+    flat = np.full(500, 0.25, dtype=np.float32)
+    eps, z, _ = thresholding.find_epsilon(torch.from_numpy(flat).cuda(), reg_level)
+    assert z == -1 and abs(eps - 0.25) < 1e-7
+    pred, eps2 = thresholding.epsilon_predict(torch.from_numpy(_score_series(5)).cuda(), torch.from_numpy(_score_series(0)).cuda(), reg_level)
+    assert pred.dtype == torch.bool and pred.any() and not pred.all()

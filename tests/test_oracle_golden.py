@@ -109,3 +109,49 @@ def test_oracle_vs_live_reference_dropout_free():
     p, r, _ = orc.model_fwd(x, params, cfg)
     assert relerr(p, p_ref.detach().numpy()) < 1e-12
     assert relerr(r, r_ref.detach().numpy()) < 1e-12
+
+
+def _score_series(seed, N=3000):
+    rng = np.random.default_rng(seed)
+    e = np.abs(rng.normal(0.1, 0.03, N))
+    for pos in rng.integers(100, N - 100, size=5):
+        e[pos:pos + rng.integers(1, 30)] += rng.uniform(0.3, 1.5)
+    return e.astype(np.float32)
+
+
+def test_threshold_oracle_equals_reference_find_epsilon():
+    """oracle/thresholding_oracle.find_epsilon vs the reference's own eval_methods.find_epsilon (eval_methods.py:186-236),
+    imported with the plotting / itertools dependencies the image lacks stubbed out."""
+    import sys, types
+    if not os.path.exists("/root/reference/eval_methods.py"):
+        pytest.skip("reference not present")
+    from oracle import thresholding_oracle as tho
+    saved = dict(sys.modules)
+    mit = types.ModuleType("more_itertools")
+    def consecutive_groups(it):
+        grp = []
+        for v in it:
+            if grp and v != grp[-1] + 1:
+                yield grp; grp = []
+            grp.append(v)
+        if grp:
+            yield grp
+    mit.consecutive_groups = consecutive_groups
+    sys.modules["more_itertools"] = mit
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.path.insert(0, "/root/reference")
+    try:
+        import eval_methods
+        for seed in range(4):
+            e = _score_series(seed)
+            for reg in (0, 1, 2):
+                assert abs(tho.find_epsilon(e, reg) - eval_methods.find_epsilon(e, reg)) < 1e-9
+        flat = np.full(500, 0.25, dtype=np.float32)
+        assert tho.find_epsilon(flat, 1) == eval_methods.find_epsilon(flat, 1)
+    finally:
+        sys.path.remove("/root/reference")
+        for name in ("eval_methods", "spot", "more_itertools", "matplotlib", "matplotlib.pyplot"):
+            if name not in saved:
+                sys.modules.pop(name, None)
