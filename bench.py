@@ -453,7 +453,10 @@ def run_ours(args):
     model = mg.MTAD_GAT(**kw).to(dev)
     model.train(c["train"])
     if c["train"]:
-        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=not args.no_graph, fused=True)
+        if args.torch_adam:
+            opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=not args.no_graph, fused=True)
+        else:
+            opt = mgt.FusedAdam(model.parameters(), lr=1e-3)       # torch.optim.Adam semantics, one launch (mtadgat_adam_step)
         step = mgt.TrainStep(model, opt, batch=B, use_graph=not args.no_graph, world_size=world,
                              target_dims=[0] if kw["out_dim"] == 1 else None, capture_comm=args.capture_comm,
                              overlap_comm=args.overlap_comm, pipeline=args.pipeline)
@@ -613,7 +616,7 @@ def run_ours(args):
                        "arithmetic": "fp32 storage/accumulate; GEMMs bf16x3 on tcgen05, recurrences fp16 operands on tcgen05",
                        "e2e_loop": "pinned host batches, H2D of batch i+1 and enqueue of step i+1 overlap step i, result of every step copied back",
                        "cuda_graph": not args.no_graph, "l2": "256 MiB buffer zeroed between timed steps",
-                       "optimizer": "torch.optim.Adam(fused) inside the step" if c["train"] else None,
+                       "optimizer": (("torch.optim.Adam(fused)" if args.torch_adam else "Adam in one launch (mtadgat_adam_step, torch.optim.Adam semantics)") + " inside the step") if c["train"] else None,
                        "comm": None if world == 1 else ("NCCL all-reduce of the gradient bucket in place, " + ("captured in the step graph" if args.capture_comm else "eager between the fwd/bwd graph and the Adam graph")),
                        "pipeline": getattr(step, "pipeline", 1)},
             "e2e": {"value": global_b / (e2e_ms * 1e-3), "unit": "windows/s", "h2d_bytes_per_step": h2d,
@@ -654,6 +657,7 @@ def main():
     ap.add_argument("--capture-comm", action="store_true", help="capture the gradient all-reduce into the step graph")
     ap.add_argument("--overlap-comm", action="store_true", help="with --capture-comm: reduce the early bucket half during backward")
     ap.add_argument("--pipeline", type=int, default=-1, help="micro-batch pipelines inside the step (-1 = auto)")
+    ap.add_argument("--torch-adam", action="store_true", help="use torch.optim.Adam(fused) instead of the library's one-launch Adam")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-ref-cuda", action="store_true")
     ap.add_argument("--sustain-s", type=float, default=2.0)

@@ -18,7 +18,9 @@
  *   - `parts` of a *_bwd: bit 0 = recurrence / data-gradient work (the critical path of backpropagation),
  *     bit 1 = parameter-gradient work (reads what bit 0 left in `scratch`).  3 = everything on `stream`;
  *     the host layer issues 1 on the main stream and 2 on a side stream so parameter gradients overlap the
- *     upstream layers' backward.
+ *     upstream layers' backward.  mtadgat_gat_bwd additionally takes 1|8 (score backward without the final dV products)
+ *     and 4 (those products alone): issued as 1|8 (main), 2 (side), 4 (main), the parameter GEMMs start as soon as the
+ *     score backward is done.
  */
 #ifndef MTADGAT_H_
 #define MTADGAT_H_
@@ -123,6 +125,13 @@ int mtadgat_rmse_pair_bwd(const float* preds, const float* y, long long n_pred, 
                           long long n_rec, const float* losses, const float* g_forecast, const float* g_recon,
                           float* dpreds, float* drecons, void* stream);
 
+/* ---- the optimiser step of the reference loop (train.py:92 torch.optim.Adam, training.py:127 optimizer.step()) over ALL
+ *      parameter tensors in one launch: table = n_tensors x 5 device int64 {param, grad, exp_avg, exp_avg_sq, numel} (fp32
+ *      tensors), step = device float holding the number of steps taken so far (incremented here; graph-replay safe).
+ *      No weight decay, no amsgrad (the reference uses neither). ---- */
+int mtadgat_adam_step(const long long* table, int n_tensors, long long max_numel, float lr, float beta1, float beta2,
+                      float eps, float* step, void* stream);
+
 /* ---- anomaly-score epilogue of Predictor.get_score (prediction.py:65-91): a_score[i][c] = |preds[i][c] - actual| +
  *      gamma |recons_last[i][c] - actual|, actual = series[n+i][target_dims ? target_dims[c] : c]; a_global[i] = mean_c
  *      (nullable).  preds, recons_last, a_score are (n_windows, out); series (N,k) with N >= n + n_windows;
@@ -134,8 +143,10 @@ int mtadgat_score_epilogue(const float* preds, const float* recons_last, const f
 /* ---- epsilon threshold (Hundman et al.) on the anomaly scores, as eval_methods.py:186-236 find_epsilon computes it
  *      (19 candidates mean + z*sd, z = 2.5 .. 11.5; anomalies dilated by +-49 indices; reg_level 0/1/2).  scores: n_scores
  *      device floats (e.g. a_global of mtadgat_score_epilogue).  out[0] = epsilon, out[1] = the winning z (-1: no
- *      candidate qualified, epsilon = max(scores)), out[2] = its score.  scratch: mtadgat_find_epsilon_scratch_doubles(). ---- */
-long long mtadgat_find_epsilon_scratch_doubles(void);
+ *      candidate qualified, epsilon = max(scores)), out[2] = its score.  scratch: mtadgat_find_epsilon_scratch_doubles(n_scores) doubles.
+ *      All sums are formed in a fixed order (no floating-point atomics): candidates with the same pruned set tie exactly,
+ *      and ties go to the last candidate as in the reference. ---- */
+long long mtadgat_find_epsilon_scratch_doubles(long long n_scores);
 int mtadgat_find_epsilon(const float* scores, long long n_scores, int reg_level, float* out, double* scratch, void* stream);
 
 /* ---- recurrence implementation: 1 (default) = persistent tcgen05/TMEM kernel, fp16 operands with fp32

@@ -45,8 +45,9 @@ SIGNATURES = {
     "mtadgat_gru_rep_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "mtadgat_gru_rep_last": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mtadgat_score_epilogue": (_I, [_P, _P, _P, _P, _I, _I, _I, _LL, _F, _P, _P, _P]),
-    "mtadgat_find_epsilon_scratch_doubles": (_LL, []),
+    "mtadgat_find_epsilon_scratch_doubles": (_LL, [_LL]),
     "mtadgat_find_epsilon": (_I, [_P, _LL, _I, _P, _P, _P]),
+    "mtadgat_adam_step": (_I, [_P, _I, _LL, _F, _F, _F, _F, _P, _P]),
     "mtadgat_linear_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _P, _U, _P]),
     "mtadgat_linear_bwd": (_I, [_P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _F, _P, _U, _I, _P]),
     "mtadgat_rmse_pair_fwd": (_I, [_P, _P, _LL, _P, _P, _LL, _P, _P, _P]),

@@ -96,6 +96,10 @@ struct DpreCols {
 
 }  // namespace
 
+namespace tcg2 {
+template <> struct FinePack<DpreT> { static constexpr bool value = true; };          // weight-gradient operands: k lines,
+template <> struct FinePack<ConvXCols> { static constexpr bool value = true; };      // K = batch x time
+}
 // ---- tensor-core loader specialisations: index decoding hoisted out of the K loop ------------------------------
 namespace tcg {
 template <bool MASKED> struct OpA<ConvShiftLoad<MASKED>> {

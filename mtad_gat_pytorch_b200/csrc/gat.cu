@@ -234,6 +234,10 @@ struct WpB {
 namespace tcg2 {
 template <> struct BatchInvariant<WpT> { static constexpr bool value = true; };     // weights: packed once, not per window
 template <> struct BatchInvariant<WpB> { static constexpr bool value = true; };
+template <> struct FinePack<NodeAT<true>> { static constexpr bool value = true; };   // few lines, K = batch x nodes
+template <> struct FinePack<NodeAT<false>> { static constexpr bool value = true; };
+template <> struct FinePack<DpqB> { static constexpr bool value = true; };
+template <> struct FinePack<DpqA> { static constexpr bool value = true; };
 }
 namespace {
 template <bool FEATURE>
@@ -1505,7 +1509,7 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
                                const unsigned long long* seed, int parts, void* stream) {
   MG_CHECK_ARG(x && lin_w && lin_b && a && out && gout && saved && scratch && dx && dlin_w && dlin_b && da,
                "gat_bwd: null pointer");
-  MG_CHECK_ARG(parts >= 1 && parts <= 3, "gat_bwd: parts must be 1 (data), 2 (parameters) or 3 (both)");
+  MG_CHECK_ARG(parts >= 1 && parts <= 15 && (parts & 7), "gat_bwd: parts is a mask of 1 (data), 2 (parameters), 4 (dV products only) [, 8]");
   cudaStream_t s = (cudaStream_t)stream;
   GatDims d = make_dims(B, n, k, E, feature, use_gatv2);
   SavedLayout L = saved_layout(d, E, 1);
@@ -1519,7 +1523,12 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
   float* attm = dbp + (((size_t)d.NC + 15) & ~(size_t)3);
   const float inv_keep = 1.f / (1.f - p_drop);
   const uint32_t strm = feature ? 1u : 2u;
+  // parts: bit 0 = data gradient (score backward + the dV products), bit 1 = parameter gradients (need only what the
+  // score backward left in scratch), bit 3 with bit 0 = score backward WITHOUT the dV products, bit 2 = the dV products
+  // alone.  The host issues 1|8 on the main stream, 2 on a side stream and 4 on the main stream again, so the parameter
+  // GEMMs start when the score backward is done instead of behind ~80 us of dV products they do not depend on.
   const bool do_data = parts & 1, do_par = parts & 2;
+  const bool do_dv = (parts & 4) || ((parts & 1) && !(parts & 8));
   // ---- bwd1 ----
   if (do_data) {
     int RB = min(d.K, 64), JT = min(d.K, 64);
@@ -1603,7 +1612,7 @@ extern "C" int mtadgat_gat_bwd(const float* x, const float* lin_w, const float* 
     MG_COUNT_LAUNCH();
   }
   // ---- data gradient: dV = A~^T dS + dPQ Wp^T ----
-  if (do_data) {
+  if (do_dv) {
     AttTA A{attm, d.K, d.Kp};
     DsB Bd{ds, d.K, d.D};
     DpqA A2{dpqt, d.NC, d.Kp};

@@ -681,6 +681,8 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_bwd_kernel(ClBwdParams P
   if (warp == 8) tc::tmem_dealloc(tbase, tmem_cols);
 }
 
+__global__ void zero_word_kernel(unsigned int* w) { *w = 0u; }
+
 __global__ void absmax2_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, long long nb,
                                unsigned int* __restrict__ out_bits) {
   float m = 0.f;
@@ -769,7 +771,10 @@ int mtadgat_gru_cl_bwd_launch(const float* gates_t, const float* out, const floa
                               int H, cudaStream_t s) {
   ClGeom g;
   if (!cl_geom(H, g)) { mtadgat_set_error("gru_cl_bwd: unsupported hidden size %d", H); return MTADGAT_ERR_UNSUPPORTED; }
-  cudaMemsetAsync(gmax_bits, 0, sizeof(unsigned int), s);
+  // the scale word is cleared by a one-thread kernel, not a memset node: inside a captured graph the kernel -> memset ->
+  // kernel hand-over in front of the BPTT showed up as a ~25 us bubble on the step's critical path
+  zero_word_kernel<<<1, 1, 0, s>>>(gmax_bits);
+  MG_COUNT_LAUNCH();
   absmax2_kernel<<<592, 256, 0, s>>>(dout, dout ? (long long)B * n * H : 0, dh_last, dh_last ? (long long)B * H : 0, gmax_bits);
   MG_COUNT_LAUNCH();
   ClBwdParams P;

@@ -55,9 +55,33 @@ __device__ __forceinline__ void store_split8_3(uint8_t* b0, uint8_t* b1, uint8_t
 template <class C> struct NFast { static constexpr bool value = true; };
 // functors whose value does not depend on the batch index z are packed once (specialise to true)
 template <class F> struct BatchInvariant { static constexpr bool value = false; };
+// pack granularity: false = one thread per (line, 32-wide k tile) -- best when consecutive K of a line are contiguous or
+// the loader amortises an index decode over the tile; true = one thread per (line, 8-wide k group) -- four times the
+// threads, for operands with few lines and a long, strided K (measured per functor on B200: NodeAT 55 -> 32 us,
+// DpreT 47 -> 27 us, DpqA 16 -> 10 us; DghTT / TiledT got 2.5x slower and stay coarse)
+template <class F> struct FinePack { static constexpr bool value = false; };
 
 // linesum (nullable): linesum[l] += sum_k operand(l, k) -- the bias gradients of the path are exactly the line sums of a
 // weight-gradient GEMM operand, so they ride along with the pack instead of costing a column-sum kernel
+// one (line, k group of 8) of a tile: 8 consecutive K of one operand line -> one 16-byte group per term
+template <class Op, class F, int R, int NS>
+__device__ __forceinline__ void pack_group(const F& f, int z, int L, int K, int ltile, int ktile, int kg, int row, uint8_t* tile,
+                                           float* __restrict__ linesum) {
+  const int l = ltile * R + row;
+  uint8_t* hi = tile;
+  uint8_t* lo = tile + Tile<R>::HALF;
+  if (l < L) {
+    const typename Op::Ctx ctx = Op::line(f, z, l);
+    float v[8];
+    Op::load8(f, ctx, z, ktile * BK + kg * 8, K, v);
+    if (NS == 3) store_split8_3(hi, lo, lo + Tile<R>::HALF, (uint32_t)(kg * R + row) * 16, v);
+    else tcg::store_split8(hi, lo, (uint32_t)(kg * R + row) * 16, v);
+    if (linesum) atomicAdd(linesum + l, ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])));
+  }
+  // rows beyond the operand's last line are never written: gemm2_kernel copies only the live rows of a partial tile
+  // and keeps the rest of its shared-memory stage at zero
+}
+
 template <class Op, class F, int R, int NS>
 __device__ __forceinline__ void pack_row(const F& f, int z, int L, int K, int ltile, int ktile, int row, uint8_t* tile,
                                          float* __restrict__ linesum) {
@@ -77,32 +101,34 @@ __device__ __forceinline__ void pack_row(const F& f, int z, int L, int K, int lt
     }
     if (linesum) atomicAdd(linesum + l, acc);
   }
-  // rows beyond the operand's last line are never written: gemm2_kernel copies only the live rows of a partial tile
-  // and keeps the rest of its shared-memory stage at zero
 }
 
-// one thread per (z, line tile, k tile, row): 32 consecutive K of one operand line -> 4 hi + 4 lo 16-byte groups.
+// thread -> work item of one operand: coarse = (z, line tile, k tile, row), fine = (z, line tile, k tile, k group, row)
+template <class Op, class F, int R, int NS, bool FINE>
+__device__ __forceinline__ void pack_item(const F& f, long long g, int L, int K, int KT, int LT, uint8_t* base,
+                                          float* __restrict__ linesum) {
+  const int row = (int)(g % R);
+  long long t1 = g / R;
+  int kg = 0;
+  if (FINE) { kg = (int)(t1 % KG); t1 /= KG; }
+  const long long tile = t1;
+  const int ktile = (int)(tile % KT);
+  const long long t2 = tile / KT;
+  uint8_t* tp = base + tile * Tile<R, NS>::BYTES;
+  if (FINE) pack_group<Op, F, R, NS>(f, (int)(t2 / LT), L, K, (int)(t2 % LT), ktile, kg, row, tp, linesum);
+  else pack_row<Op, F, R, NS>(f, (int)(t2 / LT), L, K, (int)(t2 % LT), ktile, row, tp, linesum);
+}
+
 // Threads [0, nA) pack A, the rest pack B (both counts are multiples of 32: warps never straddle).
 template <class AL, class BL, int BN, int NS>
 __global__ void __launch_bounds__(256) pack_kernel(AL A, BL Bm, int M, int N, int K, int KT, int MT, int NT, int nzA,
                                                    int nzB, uint8_t* __restrict__ Ap, uint8_t* __restrict__ Bp,
                                                    float* __restrict__ sumA, float* __restrict__ sumB) {
+  constexpr bool FA = FinePack<AL>::value, FB = FinePack<BL>::value;
   long long g = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long nA = (long long)nzA * MT * KT * BM, nB = (long long)nzB * NT * KT * BN;
-  if (g < nA) {
-    const int row = (int)(g % BM);
-    long long tile = g / BM;
-    const int ktile = (int)(tile % KT);
-    const long long t2 = tile / KT;
-    pack_row<tcg::OpA<AL>, AL, BM, NS>(A, (int)(t2 / MT), M, K, (int)(t2 % MT), ktile, row, Ap + tile * Tile<BM, NS>::BYTES, sumA);
-  } else if (g - nA < nB) {
-    g -= nA;
-    const int row = (int)(g % BN);
-    long long tile = g / BN;
-    const int ktile = (int)(tile % KT);
-    const long long t2 = tile / KT;
-    pack_row<tcg::OpB<BL>, BL, BN, NS>(Bm, (int)(t2 / NT), N, K, (int)(t2 % NT), ktile, row, Bp + tile * Tile<BN, NS>::BYTES, sumB);
-  }
+  const long long nA = (long long)nzA * MT * KT * BM * (FA ? KG : 1), nB = (long long)nzB * NT * KT * BN * (FB ? KG : 1);
+  if (g < nA) pack_item<tcg::OpA<AL>, AL, BM, NS, FA>(A, g, M, K, KT, MT, Ap, sumA);
+  else if (g - nA < nB) pack_item<tcg::OpB<BL>, BL, BN, NS, FB>(Bm, g - nA, N, K, KT, NT, Bp, sumB);
 }
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -276,7 +302,8 @@ static inline int run(int batch, int M, int N, int K, int splits_wanted, bool sp
   uint8_t* ws = mtadgat_workspace(s, a_bytes + b_bytes);
   if (!ws) { mtadgat_set_pending_error(MTADGAT_ERR_CUDA); return MTADGAT_ERR_CUDA; }
   uint8_t* Ap = ws; uint8_t* Bp = ws + a_bytes;
-  const long long nthreads = (long long)nzA * MT * KT * BM + (long long)nzB * NT * KT * BN;
+  const long long nthreads = (long long)nzA * MT * KT * BM * (FinePack<AL>::value ? KG : 1) +
+                             (long long)nzB * NT * KT * BN * (FinePack<BL>::value ? KG : 1);
   pack_kernel<AL, BL, BN, NS><<<cdiv(nthreads, 256), 256, 0, s>>>(A, Bm, M, N, K, KT, MT, NT, nzA, nzB, Ap, Bp, sumA, sumB);
   MG_COUNT_LAUNCH();
   constexpr int smem = Smem2<BN, NS>::TOTAL;

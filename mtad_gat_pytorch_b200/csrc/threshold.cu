@@ -9,10 +9,13 @@
 #include "../../include/mtadgat.h"
 
 namespace {
-constexpr int NZ = 19, HALO = 49, TB = 256;
+constexpr int NZ = 19, HALO = 49, TB = 256, G1 = 592;
 
-// scratch doubles: [0] sum, [1] sumsq, [2] max (as double);  per candidate c at 4 + 4c: cnt_below, sum_below, sumsq_below, n_dilated
-__global__ void __launch_bounds__(TB) eps_moments_kernel(const float* __restrict__ e, long long N, double* __restrict__ sc) {
+// Candidates whose pruned sets coincide must get bit-identical scores (the reference breaks such ties by taking the LAST
+// candidate: `score >= max_score`), so every sum is formed in a fixed order: per-block partials (fixed shuffle tree),
+// then one warp per quantity adds the partials lane-strided.  No floating-point atomics anywhere.
+// scratch doubles: [0] sum, [1] sumsq, [2] max | part1 [G1][3] | part2 [NZ][nblk][4] (cnt_below, sum_below, sumsq_below, n_dilated)
+__global__ void __launch_bounds__(TB) eps_moments_kernel(const float* __restrict__ e, long long N, double* __restrict__ part1) {
   __shared__ double red[3][TB / 32];
   double s = 0.0, q = 0.0, m = -INFINITY;
   for (long long i = (long long)blockIdx.x * TB + threadIdx.x; i < N; i += (long long)gridDim.x * TB) {
@@ -29,22 +32,24 @@ __global__ void __launch_bounds__(TB) eps_moments_kernel(const float* __restrict
   if (threadIdx.x == 0) {
     double ts = 0.0, tq = 0.0, tm = -INFINITY;
     for (int i = 0; i < TB / 32; ++i) { ts += red[0][i]; tq += red[1][i]; tm = fmax(tm, red[2][i]); }
-    atomicAdd(sc + 0, ts); atomicAdd(sc + 1, tq);
-    // max through an ordered-bit atomic on the double's bits (scores are finite; handles negatives)
-    unsigned long long bits = (unsigned long long)__double_as_longlong(tm);
-    bits = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
-    atomicMax(reinterpret_cast<unsigned long long*>(sc + 2), bits);
+    part1[3 * blockIdx.x + 0] = ts; part1[3 * blockIdx.x + 1] = tq; part1[3 * blockIdx.x + 2] = tm;
   }
 }
-
-__device__ __forceinline__ double decode_max(double raw) {
-  unsigned long long bits = (unsigned long long)__double_as_longlong(raw);
-  bits = (bits >> 63) ? (bits & 0x7FFFFFFFFFFFFFFFull) : ~bits;
-  return __longlong_as_double((long long)bits);
+// one warp: fixed-order sum of the G1-block partials
+__global__ void eps_moments_finish_kernel(const double* __restrict__ part1, int nblk, double* __restrict__ sc) {
+  const int l = threadIdx.x & 31;
+  double s = 0.0, q = 0.0, m = -INFINITY;
+  for (int i = l; i < nblk; i += 32) { s += part1[3 * i]; q += part1[3 * i + 1]; m = fmax(m, part1[3 * i + 2]); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if (l == 0) { sc[0] = s; sc[1] = q; sc[2] = m; }
 }
 
 // grid (chunks, NZ): block = TB consecutive indices + HALO on both sides in shared memory
-__global__ void __launch_bounds__(TB) eps_candidates_kernel(const float* __restrict__ e, long long N, double* __restrict__ sc) {
+__global__ void __launch_bounds__(TB) eps_candidates_kernel(const float* __restrict__ e, long long N, const double* __restrict__ sc,
+                                                            double* __restrict__ part2) {
   __shared__ float tile[TB + 2 * HALO];
   __shared__ double red[4][TB / 32];
   const int c = blockIdx.y;
@@ -78,41 +83,64 @@ __global__ void __launch_bounds__(TB) eps_candidates_kernel(const float* __restr
   if (threadIdx.x < 4) {
     double t = 0.0;
     for (int k = 0; k < TB / 32; ++k) t += red[threadIdx.x][k];
-    if (t != 0.0) atomicAdd(sc + 4 + 4 * c + threadIdx.x, t);
+    part2[((size_t)c * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = t;
   }
 }
 
-__global__ void eps_select_kernel(const double* __restrict__ sc, long long N, int reg_level, float* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// NZ warps: warp c adds candidate c's block partials in a fixed order; thread 0 then runs the reference's selection loop
+__global__ void __launch_bounds__(NZ * 32) eps_select_kernel(const double* __restrict__ sc, const double* __restrict__ part2,
+                                                             int nblk, long long N, int reg_level, float* __restrict__ out) {
+  __shared__ double tot[NZ][4];
+  const int c = threadIdx.x >> 5, l = threadIdx.x & 31;
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int i = l; i < nblk; i += 32) {
+    const double* p = part2 + ((size_t)c * nblk + i) * 4;
+    a[0] += p[0]; a[1] += p[1]; a[2] += p[2]; a[3] += p[3];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] += __shfl_xor_sync(0xffffffffu, a[k], o);
+  if (l == 0) { tot[c][0] = a[0]; tot[c][1] = a[1]; tot[c][2] = a[2]; tot[c][3] = a[3]; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   const double mean = sc[0] / (double)N;
   const double sd = sqrt(fmax(sc[1] / (double)N - mean * mean, 0.0));
   double best = NAN, max_score = -10000000.0; int best_c = -1;
-  for (int c = 0; c < NZ; ++c) {
-    const double cnt = sc[4 + 4 * c], s = sc[5 + 4 * c], q = sc[6 + 4 * c], nd = sc[7 + 4 * c];
+  for (int k = 0; k < NZ; ++k) {
+    const double cnt = tot[k][0], s = tot[k][1], q = tot[k][2], nd = tot[k][3];
     if (!(nd > 0.0)) continue;
     const double pm = s / cnt;                                         // NaN when nothing is below eps, as np.mean([])
     const double psd = sqrt(fmax(q / cnt - pm * pm, 0.0));
     const double denom = reg_level == 0 ? 1.0 : (reg_level == 1 ? nd : nd * nd);
     const double score = ((mean - pm) / mean + (sd - psd) / sd) / denom;
-    if (score >= max_score && nd < 0.5 * (double)N) { max_score = score; best = mean + sd * (2.5 + 0.5 * c); best_c = c; }
+    if (score >= max_score && nd < 0.5 * (double)N) { max_score = score; best = mean + sd * (2.5 + 0.5 * k); best_c = k; }
   }
-  if (best_c < 0) best = decode_max(sc[2]);
+  if (best_c < 0) best = sc[2];
   out[0] = (float)best; out[1] = best_c < 0 ? -1.f : (float)(2.5 + 0.5 * best_c); out[2] = (float)max_score;
 }
 }  // namespace
 
-extern "C" long long mtadgat_find_epsilon_scratch_doubles(void) { return 4 + 4 * NZ; }
+extern "C" long long mtadgat_find_epsilon_scratch_doubles(long long n_scores) {
+  const long long nblk = (n_scores + TB - 1) / TB;
+  return 4 + 3 * G1 + (long long)NZ * nblk * 4;
+}
 
 extern "C" int mtadgat_find_epsilon(const float* scores, long long n_scores, int reg_level, float* out, double* scratch,
                                     void* stream) {
   MG_CHECK_ARG(scores && out && scratch && n_scores > 0 && reg_level >= 0 && reg_level <= 2, "find_epsilon: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  MG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double) * (4 + 4 * NZ), s));
-  eps_moments_kernel<<<(int)min((long long)592, (n_scores + TB - 1) / TB), TB, 0, s>>>(scores, n_scores, scratch);
+  const long long nblk = (n_scores + TB - 1) / TB;
+  MG_CHECK_ARG(nblk <= 0x7fffffff, "find_epsilon: series too long");
+  const int g1 = (int)min((long long)G1, nblk);
+  double* part1 = scratch + 4; double* part2 = part1 + 3 * G1;
+  eps_moments_kernel<<<g1, TB, 0, s>>>(scores, n_scores, part1);
   MG_COUNT_LAUNCH();
-  eps_candidates_kernel<<<dim3((unsigned)((n_scores + TB - 1) / TB), NZ), TB, 0, s>>>(scores, n_scores, scratch);
+  eps_moments_finish_kernel<<<1, 32, 0, s>>>(part1, g1, scratch);
   MG_COUNT_LAUNCH();
-  eps_select_kernel<<<1, 32, 0, s>>>(scratch, n_scores, reg_level, out);
+  eps_candidates_kernel<<<dim3((unsigned)nblk, NZ), TB, 0, s>>>(scores, n_scores, scratch, part2);
+  MG_COUNT_LAUNCH();
+  eps_select_kernel<<<1, NZ * 32, 0, s>>>(scratch, part2, (int)nblk, n_scores, reg_level, out);
   MG_COUNT_LAUNCH();
   MG_CHECK_LAUNCH("find_epsilon");
   return MTADGAT_OK;

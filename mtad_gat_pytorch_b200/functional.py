@@ -130,7 +130,8 @@ PARAM_SIDE_STREAM = True
 _param_streams = {}
 _join_task = {}              # device -> id of the autograd graph task whose end-of-backward join is already queued
 _param_rr = {}
-N_PARAM_STREAMS = 2          # parameter-gradient work alternates between two side streams (4 measured no better)
+import os as _os
+N_PARAM_STREAMS = int(_os.environ.get("MTADGAT_PARAM_STREAMS", "2"))     # parameter-gradient side streams (round robin)
 
 
 def _param_stream_list(device):
@@ -154,13 +155,15 @@ def _side_stream_safe(params):
     return True
 
 
-def _run_bwd(device, call, tensors, params=()):
-    """call(parts, stream_ptr): issue the data part here, the parameter part on a side stream (when that is safe)."""
+def _run_bwd(device, call, tensors, params=(), late_data=False):
+    """call(parts, stream_ptr): issue the data part here, the parameter part on a side stream (when that is safe).
+    late_data: the entry point can defer the tail of its data part (parts 1|8 now, 4 after the side stream has forked),
+    so the parameter part does not queue behind data-gradient work it does not depend on."""
     if not PARAM_SIDE_STREAM or not _side_stream_safe(params):
         call(3, torch.cuda.current_stream(device).cuda_stream)
         return
     cur = torch.cuda.current_stream(device)
-    call(1, cur.cuda_stream)
+    call(9 if late_data else 1, cur.cuda_stream)
     streams = _param_stream_list(device)
     task = torch._C._current_graph_task_id()
     if _join_task.get(device) != task or task == -1:
@@ -181,6 +184,8 @@ def _run_bwd(device, call, tensors, params=()):
     _param_rr[device] = rr + 1
     ps.wait_stream(cur)
     call(2, ps.cuda_stream)
+    if late_data:
+        call(4, cur.cuda_stream)
     for t in tensors:
         if t is not None and t.numel() > 0:
             t.record_stream(ps)
@@ -283,7 +288,7 @@ class GatFn(torch.autograd.Function):
             x.data_ptr(), lin_w.data_ptr(), lin_b.data_ptr(), a.data_ptr(), out.data_ptr(), gout.data_ptr(),
             saved.data_ptr(), scratch.data_ptr(), dx.data_ptr(), 0, dw.data_ptr(), db.data_ptr(), da.data_ptr(),
             _ptr(dbias), B, n, k, E, feature, v2, alpha, p, seed_t.data_ptr() if has_seed else None, parts, st)),
-            (x, lin_w, lin_b, a, saved, scratch, dw, db, da, dbias), ctx.params)
+            (x, lin_w, lin_b, a, saved, scratch, dw, db, da, dbias), ctx.params, late_data=True)
         return dx, dw, db, da, dbias, None, None, None, None, None
 
 

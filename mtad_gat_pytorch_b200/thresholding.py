@@ -12,7 +12,7 @@ def find_epsilon(scores, reg_level=1):
         raise ValueError("find_epsilon: CUDA tensor expected (host arrays: use the reference's eval_methods.find_epsilon)")
     s = scores.reshape(-1).contiguous().float()
     out = torch.empty(3, dtype=torch.float32, device=s.device)
-    scratch = torch.empty(int(lib.mtadgat_find_epsilon_scratch_doubles()), dtype=torch.float64, device=s.device)
+    scratch = torch.empty(int(lib.mtadgat_find_epsilon_scratch_doubles(s.numel())), dtype=torch.float64, device=s.device)
     with torch.cuda.device(s.device):
         check(lib.mtadgat_find_epsilon(s.data_ptr(), s.numel(), int(reg_level), out.data_ptr(), scratch.data_ptr(),
                                        torch.cuda.current_stream().cuda_stream))

@@ -330,3 +330,39 @@ def test_pipelined_step_equals_unsplit_step_and_oracle(p_drop):
     print(f"[pipeline=2 fp32 p={p_drop}] worst {worst} = {errs[worst]:.3e}")
     bad = {k: v for k, v in errs.items() if not v < TOL}
     assert not bad, bad
+
+
+def test_fused_adam_equals_torch_adam_and_runs_in_the_step_graph():
+    """mtadgat_adam_step (one launch over all 28 tensors) == torch.optim.Adam(lr, betas, eps) over several steps with
+    random gradients, and TrainStep with it: graph replay == eager."""
+    import mtad_gat_pytorch_b200 as mg
+    from mtad_gat_pytorch_b200 import training as mgt
+    torch.manual_seed(4)
+    m1 = mg.MTAD_GAT(**C2).cuda()
+    m2 = mg.MTAD_GAT(**C2).cuda()
+    m2.load_state_dict(m1.state_dict())
+    o1 = mgt.FusedAdam(m1.parameters(), lr=1e-3)
+    o2 = torch.optim.Adam(m2.parameters(), lr=1e-3)
+    grads = [[torch.randn_like(p) * (10.0 ** (i - 3)) for p in m1.parameters()] for i in range(4)]
+    for gs in grads:
+        for p, q, g in zip(m1.parameters(), m2.parameters(), gs):
+            p.grad = g.clone(); q.grad = g.clone()
+        o1.step(); o2.step()
+    torch.cuda.synchronize()
+    for (nm, p), q in zip(m1.named_parameters(), m2.parameters()):
+        assert rel(p, q.detach().cpu().numpy()) < 2e-6, nm
+    assert float(o1.state[next(iter(m1.parameters()))]["step"]) == 4.0
+    # inside TrainStep: graph vs eager
+    res = {}
+    x = torch.rand(16, 100, 38, device="cuda"); y = torch.rand(16, 1, 38, device="cuda")
+    for use_graph in (True, False):
+        torch.manual_seed(5)
+        m = mg.MTAD_GAT(**dict(C2, dropout=0.0)).cuda().train()
+        step = mgt.TrainStep(m, mgt.FusedAdam(m.parameters(), lr=1e-3), batch=16, use_graph=use_graph)
+        for _ in range(3):
+            step.run_device(x, y)
+        torch.cuda.synchronize()
+        res[use_graph] = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
+        assert float(step.opt.state[next(iter(m.parameters()))]["step"]) == 3.0
+    # same kernels, same gradients up to summation order: parameters agree far below one Adam step (1e-3)
+    assert float((res[True] - res[False]).abs().max()) < 2e-4, float((res[True] - res[False]).abs().max())
