@@ -278,7 +278,10 @@ __global__ void __launch_bounds__(256) rep_build_S_kernel(const float* __restric
   const int gl = threadIdx.x & 31, g = g0 + gl;
   if (g >= G) return;
   const float* row = sw + gl * ld;
-  for (int t = threadIdx.x >> 5; t < n; t += 8) {
+  // blockIdx.y splits the time steps: 15 blocks walking all n steps made this weight-only kernel a 22 us latency chain in
+  // front of the decoder recurrence; 10x as many blocks each redo the (L2-resident) staging and finish in a few us
+  const int tpb = (n + gridDim.y - 1) / gridDim.y, t_beg = blockIdx.y * tpb, t_end = min(n, t_beg + tpb);
+  for (int t = t_beg + (threadIdx.x >> 5); t < t_end; t += 8) {
     const long long base = (long long)t * Hs;
     const int m0 = (int)(base / n);
     for (int j = 0; j < J; ++j) {
@@ -708,7 +711,7 @@ extern "C" int mtadgat_gru_rep_fwd(const float* h_src, const float* w_ih, const 
     const size_t sm = sizeof(float) * 32 * ((size_t)Hs + 1);
     MG_CHECK_ARG(sm <= 200 * 1024, "gru_rep_fwd: source width %d too large", Hs);
     if (sm > 48 * 1024) cudaFuncSetAttribute(rep_build_S_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    rep_build_S_kernel<<<cdiv(G, 32), 256, sm, s>>>(w_ih, n, Hs, G, J, S);
+    rep_build_S_kernel<<<dim3(cdiv(G, 32), min(n, 10)), 256, sm, s>>>(w_ih, n, Hs, G, J, S);
   }
   MG_COUNT_LAUNCH();
   int rc = run_recurrence_fwd(nullptr, S, h_src, b_ih, J, Hs, w_hh, b_hh, wt, out, nullptr, gates, B, n, R, s);
@@ -731,7 +734,7 @@ extern "C" int mtadgat_gru_rep_last(const float* h_src, const float* w_ih, const
     const size_t sm = sizeof(float) * 32 * ((size_t)Hs + 1);
     MG_CHECK_ARG(sm <= 200 * 1024, "gru_rep_last: source width %d too large", Hs);
     if (sm > 48 * 1024) cudaFuncSetAttribute(rep_build_S_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    rep_build_S_kernel<<<cdiv(G, 32), 256, sm, s>>>(w_ih, n, Hs, G, J, S);
+    rep_build_S_kernel<<<dim3(cdiv(G, 32), min(n, 10)), 256, sm, s>>>(w_ih, n, Hs, G, J, S);
   }
   MG_COUNT_LAUNCH();
   int rc = run_recurrence_fwd(nullptr, S, h_src, b_ih, J, Hs, w_hh, b_hh, wt, nullptr, h_last, nullptr, B, n, R, s);
