@@ -157,6 +157,10 @@ int mtadgat_get_gru_impl(void);
 /* cluster recurrence: clusters per 16-window tile, 0 = auto (default; small batches split a tile over 2 or 4
  * clusters so that more SMs work on the serial chain), or 1 / 2 / 4.  Results do not depend on it. */
 int mtadgat_set_gru_split(int split);
+/* cluster BPTT variant: 0 (default) = unit split (every CTA multiplies the whole dgh vector for its units: 30 MMAs per
+ * step), 1 = K split over the cluster (each CTA multiplies its own gate slice for all units, fp32 partial sums exchanged
+ * over DSMEM: 16 MMAs per step; measured slower on B200 -- two hand-offs per step).  Same results. */
+int mtadgat_set_gru_bptt(int ksplit);
 /* The recurrence alone (torch.nn.GRU's per-step part, modules.py:235-238) on WINDOW-TILED internals
  * T[b/16][t][channel][b%16] (B rounded up to 16): gi_t = x W_ih^T + b_ih (channels 3H), gates_t (4H: r,z,n,h_n),
  * dgi_t (3H), dghn_t (H).  mtadgat_gru_fwd / _bwd = projection GEMMs + these.  wt_scratch: 3H*H floats;

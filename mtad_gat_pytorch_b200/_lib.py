@@ -59,6 +59,7 @@ SIGNATURES = {
     "mtadgat_set_gru_impl": (_I, [_I]),
     "mtadgat_get_gru_impl": (_I, []),
     "mtadgat_set_gru_split": (_I, [_I]),
+    "mtadgat_set_gru_bptt": (_I, [_I]),
     "mtadgat_gru_recurrence_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mtadgat_gru_recurrence_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "mtadgat_tc_probe": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

@@ -109,13 +109,13 @@ template <> __device__ __forceinline__ void st_w<1>(float* p, const float* v) { 
 // (unit row, window 0) inside the destination B buffer.  All 32 lanes must call this.
 template <int WPT>
 __device__ __forceinline__ void send_quad(const float* v, float sc, bool valid, int wq, uint32_t buf_addr, uint32_t off,
-                                          uint32_t hbar_addr, int CS) {
+                                          uint32_t hbar_addr, int CS, int r0 = 0) {
   if (WPT == 4) {
     const uint32_t p0 = pack_h2(sat_h(v[0] * sc), sat_h(v[1] * sc)), p1 = pack_h2(sat_h(v[2] * sc), sat_h(v[3] * sc));
     const uint32_t o0 = __shfl_xor_sync(0xffffffffu, p0, 1), o1 = __shfl_xor_sync(0xffffffffu, p1, 1);
     if (valid && !(wq & 1)) {
       const uint32_t dst = buf_addr + off + (uint32_t)(wq >> 1) * SBO_B;
-      for (int r = 0; r < CS; ++r) st_async_v4(mapa(dst, (uint32_t)r), p0, p1, o0, o1, mapa(hbar_addr, (uint32_t)r));
+      for (int r = r0; r < r0 + CS; ++r) st_async_v4(mapa(dst, (uint32_t)r), p0, p1, o0, o1, mapa(hbar_addr, (uint32_t)r));
     }
   } else if (WPT == 2) {
     const uint32_t p0 = pack_h2(sat_h(v[0] * sc), sat_h(v[1] * sc));
@@ -123,7 +123,7 @@ __device__ __forceinline__ void send_quad(const float* v, float sc, bool valid, 
                    p3 = __shfl_down_sync(0xffffffffu, p0, 3);
     if (valid && wq == 0) {
       const uint32_t dst = buf_addr + off;
-      for (int r = 0; r < CS; ++r) st_async_v4(mapa(dst, (uint32_t)r), p0, p1, p2, p3, mapa(hbar_addr, (uint32_t)r));
+      for (int r = r0; r < r0 + CS; ++r) st_async_v4(mapa(dst, (uint32_t)r), p0, p1, p2, p3, mapa(hbar_addr, (uint32_t)r));
     }
   } else {
     const uint32_t p0 = (uint32_t)__half_as_ushort(__float2half_rn(sat_h(v[0] * sc)));
@@ -131,7 +131,7 @@ __device__ __forceinline__ void send_quad(const float* v, float sc, bool valid, 
                    p3 = __shfl_down_sync(0xffffffffu, p0, 3);
     if (valid && wq == 0) {
       const uint32_t dst = buf_addr + off;
-      for (int r = 0; r < CS; ++r)
+      for (int r = r0; r < r0 + CS; ++r)
         st_async_v2(mapa(dst, (uint32_t)r), p0 | (p1 << 16), p2 | (p3 << 16), mapa(hbar_addr, (uint32_t)r));
     }
   }
@@ -681,6 +681,278 @@ __global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_bwd_kernel(ClBwdParams P
   if (warp == 8) tc::tmem_dealloc(tbase, tmem_cols);
 }
 
+
+// ==========================================================================================================
+// BPTT, K split over the cluster.
+// gru_cl_bwd_kernel gives every CTA the W_hh^T rows of ITS units and the whole 3H-long dgh vector: 30 dependent MMAs per
+// step (K = 3*Hp = 480) behind a cluster-wide broadcast of dgh.  Here CTA r keeps the COLUMNS of W_hh^T that belong to
+// its own gate slice -- k = (gate, unit in [r*Uc, r*Uc+Uc)), K_local = 3*Uc = 120 -> 128 -- for ALL units (M = Hp = 160:
+// one M=128 and one M=64 tile, both resident in tensor memory), so the B operand of a step is the CTA's OWN dgh slice
+// (written locally, no broadcast before the MMAs) and a step is 2 x 8 = 16 MMAs.  What crosses the cluster is the
+// result: every CTA holds partial sums for all units and sends the rows of CTA q's units to q as fp32 (st.async with
+// complete_tx on q's mbarrier); q adds the CS partials.  16 instead of 30 MMAs on the dependency chain and fp32 partials
+// instead of fp16 operands on the wire -- but TWO asynchronous hand-offs per step (local dgh -> MMA issuer, partial rows
+// -> owners) instead of one.  Measured on B200 (H = 150, batch 256): 2.14 us per step against 1.77 us for the unit-split
+// kernel, so this variant is opt-in (mtadgat_set_gru_bptt(1)); it is kept, tested against the other two
+// implementations, as the measured answer to "does halving the MMA chain pay?" -- it does not: the chain is dominated by
+// hand-off and wake-up latencies, not by the MMAs.
+// ==========================================================================================================
+static size_t cl_bwd2_smem(int H, int NW) {
+  ClGeom g; cl_geom(H, g);
+  const int Kl = (3 * g.Uc + 15) & ~15, KCl = Kl / 8;
+  return (size_t)KCl * 192 * 16 + 2 * (size_t)KCl * LBO_B + 2 * (size_t)g.CS * g.Uc * NW * 4 + 128;
+}
+static bool cl_bwd2_supported(int H) {
+  ClGeom g;
+  if (!cl_geom(H, g)) return false;
+  const int Hp = g.CS * g.Uc, Kl = (3 * g.Uc + 15) & ~15;
+  return Hp <= 192 && 32 + Kl <= 256 && cl_bwd2_smem(H, 16) <= 200 * 1024;
+}
+
+template <int WPT>
+__global__ void __launch_bounds__(CL_THREADS, 2) gru_cl_bwd2_kernel(ClBwdParams P) {
+  constexpr int NW = 4 * WPT, SPLIT = NB / NW;
+  static_assert(WPT == 2 || WPT == 4, "K-split BPTT: 8 or 16 windows per cluster");
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int H = P.H, G = 3 * H, n = P.n, CS = P.CS, Uc = P.Uc;
+  const int Hp = CS * Uc;                                   // padded unit count = rows of the partial result
+  const int Kl = (3 * Uc + 15) & ~15, KCl = Kl / 8, nkc = Kl / 16;
+  const bool two_tiles = Hp > 128;
+  const int lboA = 192 * 16;
+  constexpr int D1 = 0, D2 = 16, A1 = 32;                   // tensor-memory columns: accumulators, then the two A tiles
+  const int A2 = A1 + Kl / 2;
+  uint8_t* sA = smem_raw;                                   // staging [KCl][192 rows][16 B]
+  uint8_t* sB = sA + (size_t)KCl * lboA;                    // [2][KCl][256 B] : this CTA's dgh slice, NW windows
+  float* sR = reinterpret_cast<float*>(sB + 2 * (size_t)KCl * LBO_B);      // [2][CS][Uc][NW] partial sums received
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sR + 2 * (size_t)CS * Uc * NW);
+  uint64_t* acc_bar = bars;        // MMA commit -> drain warps
+  uint64_t* h_bar = bars + 1;      // own dgh slice landed (st.async tx bytes) -> MMA issuer
+  uint64_t* p_bar = bars + 2;      // [2], alternating by step: all CTAs' partial rows landed -> epilogue (a peer that runs a
+                                   // step ahead completes bytes on the OTHER barrier, never on the phase still being collected)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cid = blockIdx.x / CS;
+  const int tile = cid / SPLIT, wo = (cid % SPLIT) * NW, b0 = tile * NB + wo;
+  const int u0 = rank * Uc, nu = max(0, min(Uc, H - u0));
+
+  // ---- A_r[u'][kk = gate*Uc + i] = W_hh[gate*H + u0 + i][u']  (u' fastest: coalesced reads of W_hh rows) ----
+  for (int base = 0; base < 192 * Kl; base += 8 * CL_THREADS) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * CL_THREADS + tid;
+      const int kk = idx / 192, up = idx - kk * 192;
+      const int gate = kk / Uc, i = kk - gate * Uc;
+      v[j] = (idx < 192 * Kl && gate < 3 && i < nu && up < H) ? __ldg(P.w_hh + ((size_t)gate * H + u0 + i) * H + up) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = base + j * CL_THREADS + tid;
+      const int kk = idx / 192, up = idx - kk * 192;
+      if (idx < 192 * Kl)
+        *reinterpret_cast<__half*>(sA + (size_t)(kk >> 3) * lboA + (size_t)up * 16 + (kk & 7) * 2) = __float2half_rn(v[j]);
+    }
+  }
+  for (int idx = tid; idx < (2 * KCl * LBO_B) / 4; idx += CL_THREADS) reinterpret_cast<uint32_t*>(sB)[idx] = 0u;
+  if (tid == 0) {
+    tc::mbar_init(acc_bar, 1);
+    tc::mbar_init(h_bar, 1);
+    tc::mbar_init(p_bar, 1);
+    tc::mbar_init(p_bar + 1, 1);
+    tc::fence_mbar_init();
+  }
+  const int tmem_cols = tmem_cols_for(A1, Kl);              // A1 + 2 * (Kl / 2)
+  if (warp == 8) tc::tmem_alloc(tmem_slot, tmem_cols);
+  fence_proxy_async_all();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  if (warp < 8) {
+    const int q = warp & 3;
+    const int c_beg = (warp >> 2) ? nkc / 2 : 0, c_end = (warp >> 2) ? nkc : nkc / 2;
+    for (int c = c_beg; c < c_end; ++c) {
+      {   // tile 1: rows 0..127, row = TMEM lane
+        const int row = q * 32 + lane;
+        const uint4 lo = *reinterpret_cast<const uint4*>(sA + (size_t)(2 * c) * lboA + (size_t)row * 16);
+        const uint4 hi = *reinterpret_cast<const uint4*>(sA + (size_t)(2 * c + 1) * lboA + (size_t)row * 16);
+        const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tc::tmem_st8(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(A1 + c * 8), r);
+      }
+      if (two_tiles) {   // tile 2 (M = 64): row i of the tile lives in lane 32*(i/16) + i%16; the other lanes hold zeros
+        const int row = 128 + q * 16 + (lane & 15);
+        uint4 lo = *reinterpret_cast<const uint4*>(sA + (size_t)(2 * c) * lboA + (size_t)row * 16);
+        uint4 hi = *reinterpret_cast<const uint4*>(sA + (size_t)(2 * c + 1) * lboA + (size_t)row * 16);
+        if (lane >= 16) { lo = make_uint4(0u, 0u, 0u, 0u); hi = lo; }
+        const uint32_t r[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        tc::tmem_st8(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(A2 + c * 8), r);
+      }
+    }
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc::tc_fence_after();
+
+  const uint32_t tx_h = (uint32_t)3 * nu * NW * 2;                       // own dgh slice per step
+  const uint32_t tx_p = (uint32_t)CS * nu * NW * 4;                      // partial rows of this CTA's units from every CTA
+  if (warp == 8) {
+    // ================= MMA issuer =================
+    // N = 16 for both tiles (an M = 128 MMA needs N % 16 == 0): with 8 live windows the upper 8 B columns stay zero
+    const uint32_t idesc1 = tc::make_idesc_f16(128, NB, 0, /*b_mn_major=*/1);
+    const uint32_t idesc2 = tc::make_idesc_f16(64, NB, 0, /*b_mn_major=*/1);
+    const uint32_t binc = (uint32_t)(2 * LBO_B) >> 4;
+    if (n > 1 && tc::elect_one()) mbar_arrive_expect_tx(h_bar, tx_h);
+    __syncwarp();
+    for (int it = 0; it < n - 1; ++it) {
+      tc::mbar_wait(h_bar, it & 1);
+      tc::tc_fence_after();
+      const uint64_t bd0 = tc::make_smem_desc(tc::smem_u32(sB) + (uint32_t)((it & 1) * KCl * LBO_B), LBO_B, SBO_B);
+      uint32_t blo = (uint32_t)bd0;
+      const uint32_t bhi = (uint32_t)(bd0 >> 32);
+      for (int kc = 0; kc < nkc; ++kc) {
+        if (tc::elect_one()) {
+          tc::mma_f16_ts(tbase + D1, tbase + (uint32_t)(A1 + 8 * kc), blo, bhi, idesc1, kc > 0 ? 1u : 0u);
+          if (two_tiles) tc::mma_f16_ts(tbase + D2, tbase + (uint32_t)(A2 + 8 * kc), blo, bhi, idesc2, kc > 0 ? 1u : 0u);
+        }
+        blo += binc;
+      }
+      if (tc::elect_one()) {
+        tc::mma_commit(acc_bar);
+        if (it + 1 < n - 1) mbar_arrive_expect_tx(h_bar, tx_h);
+      }
+      __syncwarp();
+    }
+  } else if (warp < EPI_THREADS / 32) {
+    const int i = tid >> 2, wq = tid & 3, wb = WPT * wq;
+    const bool valid = i < nu;
+    const int u = u0 + i;
+    const float gmax = __uint_as_float(*P.gmax_bits);
+    const float scale = gmax > 0.f ? exp2f(floorf(log2f(64.f / gmax))) : 1.f;
+    const float inv_scale = 1.f / scale;
+    float dhz[WPT];
+#pragma unroll
+    for (int w = 0; w < WPT; ++w) dhz[w] = 0.f;
+    // rows of the LOCAL B operand: kk = gate*Uc + i
+    const uint32_t off0 = (uint32_t)(i >> 3) * LBO_B + (uint32_t)(i & 7) * 16;
+    const uint32_t off1 = (uint32_t)((Uc + i) >> 3) * LBO_B + (uint32_t)((Uc + i) & 7) * 16;
+    const uint32_t off2 = (uint32_t)((2 * Uc + i) >> 3) * LBO_B + (uint32_t)((2 * Uc + i) & 7) * 16;
+    const uint32_t sB_addr = tc::smem_u32(sB), hbar_addr = tc::smem_u32(h_bar);
+    const uint32_t sR_addr = tc::smem_u32(sR), pbar_addr = tc::smem_u32(p_bar);
+    const size_t gt_step = (size_t)4 * H * 16, gi_step = (size_t)G * 16, gn_step = (size_t)H * 16;
+    const float* gt_p = valid ? P.gates + ((size_t)tile * n * 4 * H + u) * 16 + wo + wb : nullptr;
+    float* dgi_p = valid ? P.dgi + ((size_t)tile * n * G + u) * 16 + wo + wb : nullptr;
+    float* dgn_p = valid ? P.dghn + ((size_t)tile * n * H + u) * 16 + wo + wb : nullptr;
+    const int nvalid_w = max(0, min(WPT, P.B - (b0 + wb)));
+    const size_t row0 = (size_t)(b0 + wb) * n;
+    const uint32_t tlane = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+
+    float dh[WPT], hp[WPT], r[WPT], z[WPT], nn[WPT], hn[WPT];
+    auto load_step = [&](int tt) {
+      if (valid) {
+        const float* gq = gt_p + (size_t)tt * gt_step;
+        ldg_w<WPT>(gq, r); ldg_w<WPT>(gq + (size_t)H * 16, z); ldg_w<WPT>(gq + (size_t)2 * H * 16, nn);
+        ldg_w<WPT>(gq + (size_t)3 * H * 16, hn);
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) {
+          float v = 0.f, p = 0.f;
+          if (w < nvalid_w) {
+            size_t o = (row0 + (size_t)w * n + tt) * H + u;
+            if (P.dout) v = __ldg(P.dout + o);
+            if (tt == n - 1 && P.dh_last) v += __ldg(P.dh_last + (size_t)(b0 + wb + w) * H + u);
+            if (tt > 0) p = __ldg(P.out + o - H);
+          }
+          dh[w] = v; hp[w] = p;
+        }
+      } else {
+#pragma unroll
+        for (int w = 0; w < WPT; ++w) { dh[w] = 0.f; hp[w] = 0.f; r[w] = 0.f; z[w] = 0.f; nn[w] = 0.f; hn[w] = 0.f; }
+      }
+    };
+    load_step(n - 1);
+
+    // send one partial row (unit up, NW fp32 window values) to the CTA that owns the unit
+    auto send_row = [&](int up, const float* v, int par) {
+      const int q = up / Uc, i2 = up - q * Uc;
+      const uint32_t dst = sR_addr + (uint32_t)(((par * CS + rank) * Uc + i2) * NW) * 4;
+      const uint32_t rdst = mapa(dst, (uint32_t)q), rbar = mapa(pbar_addr + 8u * (uint32_t)par, (uint32_t)q);
+#pragma unroll
+      for (int c = 0; c < NW; c += 4)
+        st_async_v4(rdst + (uint32_t)c * 4, __float_as_uint(v[c]), __float_as_uint(v[c + 1]), __float_as_uint(v[c + 2]),
+                    __float_as_uint(v[c + 3]), rbar);
+    };
+
+    for (int t = n - 1; t >= 0; --t) {
+      const int it = n - 1 - t;
+      if (it > 0) {
+        const int par = (it - 1) & 1;
+        if (warp < 4) {
+          // drain the partial sums of MMA #(it-1) and ship each row to its owner
+          tc::mbar_wait(acc_bar, (it - 1) & 1);
+          tc::tc_fence_after();
+          float v1[NW], v2[NW];
+          if (NW == 16) { tc::tmem_ld16(tlane + D1, v1); if (two_tiles) tc::tmem_ld16(tlane + D2, v2); }
+          else { tc::tmem_ld8(tlane + D1, v1); if (two_tiles) tc::tmem_ld8(tlane + D2, v2); }
+          tc::tmem_ld_wait();
+          tc::tc_fence_before();
+          const int up1 = warp * 32 + lane;
+          if (up1 < H) send_row(up1, v1, par);
+          if (two_tiles && lane < 16) {
+            const int up2 = 128 + warp * 16 + lane;
+            if (up2 < H) send_row(up2, v2, par);
+          }
+        }
+        tc::mbar_wait(p_bar + par, ((it - 1) >> 1) & 1);
+        if (valid) {
+          float acc[WPT];
+#pragma unroll
+          for (int w = 0; w < WPT; ++w) acc[w] = 0.f;
+          for (int s_ = 0; s_ < CS; ++s_) {
+            float a[WPT];
+            ld_w<WPT>(sR + (size_t)((par * CS + s_) * Uc + i) * NW + wb, a);
+#pragma unroll
+            for (int w = 0; w < WPT; ++w) acc[w] += a[w];
+          }
+#pragma unroll
+          for (int w = 0; w < WPT; ++w) dh[w] += dhz[w] + acc[w] * inv_scale;
+        }
+      }
+      float dpr[WPT], dpz[WPT], dpn[WPT], dgn[WPT];
+#pragma unroll
+      for (int w = 0; w < WPT; ++w) {
+        float d = dh[w];
+        float dn = d * (1.f - z[w]);
+        float dz = d * (hp[w] - nn[w]);
+        dpn[w] = dn * (1.f - nn[w] * nn[w]);
+        dpz[w] = dz * z[w] * (1.f - z[w]);
+        dpr[w] = dpn[w] * hn[w] * r[w] * (1.f - r[w]);
+        dgn[w] = dpn[w] * r[w];
+        dhz[w] = d * z[w];
+      }
+      if (t > 0) {
+        // arm the phase that will collect the partial sums of MMA #it BEFORE any CTA can have produced them
+        if (tid == 0) mbar_arrive_expect_tx(p_bar + (it & 1), tx_p);
+        const uint32_t buf = sB_addr + (uint32_t)((it & 1) * KCl * LBO_B);
+        send_quad<WPT>(dpr, scale, valid, wq, buf, off0, hbar_addr, 1, rank);
+        send_quad<WPT>(dpz, scale, valid, wq, buf, off1, hbar_addr, 1, rank);
+        send_quad<WPT>(dgn, scale, valid, wq, buf, off2, hbar_addr, 1, rank);
+      }
+      if (valid) {
+        float* q = dgi_p + (size_t)t * gi_step;
+        st_w<WPT>(q, dpr); st_w<WPT>(q + (size_t)H * 16, dpz); st_w<WPT>(q + (size_t)2 * H * 16, dpn);
+        st_w<WPT>(dgn_p + (size_t)t * gn_step, dgn);
+      }
+      if (t > 0) load_step(t - 1);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 8) tc::tmem_dealloc(tbase, tmem_cols);
+}
+
 __global__ void zero_word_kernel(unsigned int* w) { *w = 0u; }
 
 __global__ void absmax2_kernel(const float* __restrict__ a, long long na, const float* __restrict__ b, long long nb,
@@ -723,6 +995,9 @@ static int launch_cluster(Kern kern, const Params& P, int nblocks, int cs, size_
 }
 
 static long long* g_dbg = nullptr;
+static int g_bptt_ksplit = 0;         // 0 = unit-split BPTT (30 MMAs per step, default), 1 = K-split (16 MMAs per step: correct, but
+                                      // measured SLOWER on B200 -- 214 vs 177 us per launch at H = 150, batch 256: the second
+                                      // asynchronous hand-off per step costs more than the 14 MMAs it saves)
 static int g_split = 0;               // 0 = auto, else clusters per 16-window tile (1, 2 or 4)
 
 // clusters per 16-window tile: split the tile while the grid still fits ~2 CTAs per SM
@@ -736,6 +1011,11 @@ static int pick_split(int B, int CS) {
 }  // namespace
 
 extern "C" void mtadgat_gru_debug_buffer(long long* dev_ptr) { g_dbg = dev_ptr; }
+extern "C" int mtadgat_set_gru_bptt(int ksplit) {
+  MG_CHECK_ARG(ksplit == 0 || ksplit == 1, "set_gru_bptt: 0 (unit-split, 30 MMAs per step) or 1 (K-split, 16 MMAs per step)");
+  g_bptt_ksplit = ksplit;
+  return MTADGAT_OK;
+}
 extern "C" int mtadgat_set_gru_split(int split) {
   MG_CHECK_ARG(split == 0 || split == 1 || split == 2 || split == 4, "set_gru_split: 0 (auto), 1, 2 or 4 clusters per 16-window tile");
   g_split = split;
@@ -781,6 +1061,10 @@ int mtadgat_gru_cl_bwd_launch(const float* gates_t, const float* out, const floa
   P.gates = gates_t; P.out = out; P.w_hh = w_hh; P.dout = dout; P.dh_last = dh_last; P.gmax_bits = gmax_bits;
   P.dgi = dgi_t; P.dghn = dghn_t; P.B = B; P.n = n; P.H = H; P.CS = g.CS; P.Uc = g.Uc;
   const int split = pick_split(B, g.CS), nblocks = cdiv(B, NB) * split * g.CS;
+  if (g_bptt_ksplit && split <= 2 && cl_bwd2_supported(H)) {
+    if (split == 2) return launch_cluster(gru_cl_bwd2_kernel<2>, P, nblocks, g.CS, cl_bwd2_smem(H, 8), s);
+    return launch_cluster(gru_cl_bwd2_kernel<4>, P, nblocks, g.CS, cl_bwd2_smem(H, 16), s);
+  }
   const size_t smem = cl_bwd_smem(H);
   if (split == 4) return launch_cluster(gru_cl_bwd_kernel<1, 2>, P, nblocks, g.CS, smem, s);
   if (split == 2) return launch_cluster(gru_cl_bwd_kernel<2, 2>, P, nblocks, g.CS, smem, s);

@@ -463,6 +463,13 @@ def set_gru_split(split):
     check(lib.mtadgat_set_gru_split(int(split)))
 
 
+def set_gru_bptt(name):
+    """'unitsplit' (default): every CTA of the cluster multiplies the whole dgh vector for its units (30 MMAs per step);
+    'ksplit': K range split over the CTAs (16 MMAs per step, fp32 partial sums over DSMEM) -- same results, measured
+    slower on B200 (two asynchronous hand-offs per step)."""
+    check(lib.mtadgat_set_gru_bptt({"unitsplit": 0, "ksplit": 1}[name]))
+
+
 def set_gemm_impl(name):
     """'tc' (default): tcgen05 bf16x3 GEMMs on packed operands; 'tc_gather': same arithmetic, operands gathered inside
     the GEMM kernel; 'fp32': SIMT fp32 GEMMs."""

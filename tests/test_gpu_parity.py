@@ -573,3 +573,39 @@ def test_fused_gat_kernel_equals_projection_gemm_plus_score_kernel(shape):
                 for u, v in zip(b_[3], a[3])]
         print(f"[fused vs split {cls.__name__} k={k} n={n} v2={v2}] " + " ".join(f"{e:.1e}" for e in errs))
         assert max(errs) < 1e-4, errs          # tiny shapes: gradients near the 1e-6 floor of rel()
+
+
+@pytest.mark.parametrize("H,B", [(150, 256), (150, 40), (64, 33), (100, 16), (32, 7)])
+def test_ksplit_bptt_equals_unit_split_bptt_and_fp32(H, B):
+    """The K-split cluster BPTT (each CTA multiplies its own gate slice for all units, fp32 partial sums exchanged over
+    DSMEM, 16 MMAs per step) against the unit-split kernel (30 MMAs per step) and the fp32 SIMT recurrence: encoder-style
+    (only dh_last) and decoder-style (gradient on every step's output) backward."""
+    import mtad_gat_pytorch_b200 as mg
+    torch.manual_seed(H + B)
+    n, I = 100, 114
+    layer = mg.RNNDecoder(I, H, 1, 0.0).cuda()
+    x = torch.randn(B, n, I, device="cuda") * 0.5
+    go = torch.randn(B, n, H, device="cuda")
+    res = {}
+    try:
+        for tag in ("fp32", "unitsplit", "ksplit"):
+            mg.set_gru_impl("fp32" if tag == "fp32" else "tc")
+            if tag != "fp32":
+                mg.set_gru_bptt(tag)
+            for style in ("all", "last"):
+                layer.zero_grad(set_to_none=True)
+                xi = x.clone().requires_grad_(True)
+                out = layer(xi)
+                if style == "all":
+                    out.backward(go)
+                else:
+                    out[:, -1, :].backward(go[:, -1, :])
+                torch.cuda.synchronize()
+                res[(tag, style)] = [xi.grad.clone()] + [p.grad.clone() for p in layer.parameters()]
+    finally:
+        mg.set_gru_bptt("unitsplit"); mg.set_gru_impl("tc")
+    for style in ("all", "last"):
+        e_ku = max(rel(a, b.cpu().numpy()) for a, b in zip(res[("ksplit", style)], res[("unitsplit", style)]))
+        e_k32 = max(rel(a, b.cpu().numpy()) for a, b in zip(res[("ksplit", style)], res[("fp32", style)]))
+        print(f"[bptt H={H} B={B} {style}] ksplit vs unitsplit {e_ku:.1e}, ksplit vs fp32 {e_k32:.1e}")
+        assert e_ku < 3e-4 and e_k32 < TOL, (style, e_ku, e_k32)
