@@ -9,6 +9,9 @@
  * Conventions
  *   - every pointer is a DEVICE pointer to contiguous fp32 unless stated otherwise; sizes are ints
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *   - one device per process (the scaling model is one process per GPU): the mode switches (mtadgat_set_*), the per-stream
+ *     pack workspaces and the kernels' one-time attribute setup are process-wide and assume the calling thread's current
+ *     device is the one the pointers live on
  *   - return value 0 = ok; non-zero = error, message via mtadgat_last_error() (thread-local)
  *   - `saved` buffers are written by *_fwd and must be handed unchanged to the matching *_bwd;
  *     `scratch` buffers are temporaries; sizes (in floats) come from the *_floats() queries

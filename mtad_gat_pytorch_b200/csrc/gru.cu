@@ -562,7 +562,7 @@ static int run_recurrence_fwd(const float* gi_t, const float* S, const float* hs
                               float* gates_t, int B, int n, int H, cudaStream_t s) {
   if (g_gru_impl == 1 && mtadgat_gru_cl_supported(H, gi_t ? 0 : Hs))
     return mtadgat_gru_cl_fwd_launch(gi_t, S, hsrc, b_ih, J, Hs, w_hh, b_hh, out, h_last, gates_t, B, n, H, s);
-  if (g_gru_impl >= 1 && mtadgat_gru_tc_supported(H))
+  if (g_gru_impl >= 1 && mtadgat_gru_tc_supported(H, gi_t ? 0 : Hs))
     return mtadgat_gru_tc_fwd_launch(gi_t, S, hsrc, b_ih, J, Hs, w_hh, b_hh, out, h_last, gates_t, B, n, H, s);
   launch_transpose(w_hh, wt_scratch, 3 * H, H, s);
   GruFwdParams P;
@@ -576,7 +576,7 @@ static int run_recurrence_bwd(const float* gates_t, const float* out, const floa
                               cudaStream_t s) {
   if (g_gru_impl == 1 && mtadgat_gru_cl_supported(H, 0))
     return mtadgat_gru_cl_bwd_launch(gates_t, out, w_hh, dout, dh_last, gmax, dgi_t, dghn_t, B, n, H, s);
-  if (g_gru_impl >= 1 && mtadgat_gru_tc_supported(H))
+  if (g_gru_impl >= 1 && mtadgat_gru_tc_supported(H, 0))
     return mtadgat_gru_tc_bwd_launch(gates_t, out, w_hh, dout, dh_last, gmax, dgi_t, dghn_t, B, n, H, s);
   GruBwdParams P;
   P.gates = gates_t; P.out = out; P.w_hh = w_hh; P.dout = dout; P.dh_last = dh_last; P.dgi = dgi_t; P.dghn = dghn_t;

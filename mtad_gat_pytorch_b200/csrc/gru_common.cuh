@@ -22,7 +22,7 @@ __device__ __forceinline__ void tiled_row_decode(int r, int n, int& b, int& t) {
 __device__ __forceinline__ size_t tiled_rc(int r, int c, int C) { return ((size_t)(r >> 4) * C + c) * 16 + (r & 15); }
 
 // ---- tensor-core path (gru_tc.cu) ----
-int mtadgat_gru_tc_supported(int H);
+int mtadgat_gru_tc_supported(int H, int Hs_rep);
 int mtadgat_gru_tc_fwd_launch(const float* gi_t, const float* S, const float* hsrc, const float* b_ih, int J, int Hs,
                               const float* w_hh, const float* b_hh, float* out, float* h_last, float* gates_t, int B,
                               int n, int H, cudaStream_t s);

@@ -572,9 +572,11 @@ __global__ void __launch_bounds__(256, 1) tc_mma_bench_kernel(int ntiles, int kc
 }  // namespace
 
 // Called from gru.cu ------------------------------------------------------------------------------------------
-int mtadgat_gru_tc_supported(int H) {
+// Hs_rep: width of the decoder's repeat source staged by the forward kernel (0 for a plain GRU layer): the shared-memory
+// need depends on it, so an unsupported (H, Hs) falls through to the fp32 kernels instead of failing at launch
+int mtadgat_gru_tc_supported(int H, int Hs_rep) {
   if (H < 8 || H > 256) return 0;
-  return fwd_dims(H, 256).smem <= 224 * 1024 && bwd_dims(H).smem <= 224 * 1024;
+  return fwd_dims(H, Hs_rep).smem <= 224 * 1024 && bwd_dims(H).smem <= 224 * 1024;
 }
 
 int mtadgat_gru_tc_fwd_launch(const float* gi_t, const float* S, const float* hsrc, const float* b_ih, int J, int Hs,
