@@ -80,7 +80,9 @@ class FusedAdam:
     """torch.optim.Adam(lr, betas, eps) semantics (no weight decay, no amsgrad -- train.py:92 uses neither) for CUDA
     fp32 parameters, as ONE kernel launch over all tensors (`mtadgat_adam_step`): torch's multi-tensor Adam takes 38 us
     for this model's 28 small tensors at the tail of every step, this one ~5 us.  Graph-capturable (the step counter lives
-    on the device).  Exposes `.state[p] = {step, exp_avg, exp_avg_sq}`, `.param_groups`, `.zero_grad`, `.step`."""
+    on the device; lr / betas / eps are kernel arguments, so a captured graph keeps the values it was captured with --
+    re-capture after changing them; the reference's loop never does, training.py:106-127).  Exposes
+    `.state[p] = {step, exp_avg, exp_avg_sq}`, `.param_groups`, `.zero_grad`, `.step`."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         self.params = [p for p in params if p.requires_grad]
