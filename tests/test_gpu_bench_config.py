@@ -75,8 +75,8 @@ def test_c2_batch256_tc_train_mode_all_gradients_vs_oracle():
     assert not bad, bad
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tc"])
-def test_train_step_graph_vs_eager_vs_oracle(mode):
+@pytest.mark.parametrize("mode,optim", [("fp32", "torch"), ("tc", "torch"), ("tc", "fused")])
+def test_train_step_graph_vs_eager_vs_oracle(mode, optim):
     """TrainStep(use_graph=True) == TrainStep(use_graph=False) == the oracle + numpy Adam over 3 optimisation steps
     with fresh dropout masks per step (seed advanced on the device, also under graph replay), on the C2 model.
     Step-1 gradients are not observable through TrainStep, so what is compared is the loss of every step (1e-3) and
@@ -96,7 +96,10 @@ def test_train_step_graph_vs_eager_vs_oracle(mode):
     results = {}
     for use_graph in (True, False):
         m = build(C2, params0, train=True)
-        opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=use_graph, fused=True)
+        if optim == "fused":          # what bench.py runs: the library's one-launch Adam on the GradBucket's gradient views
+            opt = mgt.FusedAdam(m.parameters(), lr=1e-3)
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=use_graph, fused=True)
         step = mgt.TrainStep(m, opt, batch=B, use_graph=use_graph)
         mg.manual_seed(S)
         losses = []
